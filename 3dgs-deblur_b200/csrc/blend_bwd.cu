@@ -1,0 +1,291 @@
+// Blur / rolling-shutter alpha-blend, backward.  Semantics of
+// /root/reference/gsplat/gsplat/cuda/csrc/backward.cu:143-369, including the
+// reference's 0.99 alpha clamp (backward.cu:275; the forward uses 0.999) and abs-grad per
+// pixel-sample contribution (backward.cu:328-329).
+//
+// How it differs from the reference kernel:
+//   * one back-to-front walk of the tile list for all S samples (per-sample T, running colour dot
+//     product and last-contributor index live in registers) instead of S walks;
+//   * per-Gaussian gradients are accumulated over the S samples in registers BEFORE the warp
+//     reduction: S x fewer shuffles and atomics than backward.cu:334-365;
+//   * the 13 per-Gaussian sums are reduced with a 16-shuffle transposing butterfly (instead of
+//     13 x 5 shuffles) that leaves each sum on its own lane, so the 13 atomics issue as one
+//     predicated RED instruction instead of 13 serial ones from lane 0;
+//   * the same per-warp rectangle cull and TMA-bulk staged 64-byte records as the forward.
+// Bound: FP32 issue, MUFU, SHFL and L2 atomic throughput -- not HBM; see DESIGN.md.
+#include "blend_common.cuh"
+
+namespace b200 {
+
+struct BlendBwdParams {
+    BlendGeom g;
+    const int32_t *ids_sorted;
+    const int2 *tile_bins;
+    const PackedGaussian *packed;
+    const float *background;
+    const float *final_Ts;
+    const int32_t *final_idx;
+    const float *v_out;        // (H,W,3)
+    const float *v_out_alpha;  // (H,W)
+    float *v_xy, *v_xy_abs, *v_pix_vel, *v_conic, *v_rgb, *v_opac;
+};
+
+// Sum 16 per-lane values across the warp; lane L returns the total of value (L >> 1) & 15.
+__device__ __forceinline__ float butterfly16(const float (&v)[16], int lane) {
+    float w8[8], w4[4], w2[2], w1;
+    bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = up ? w8[i] : w8[i + 4], keep = up ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = up ? w4[i] : w4[i + 2], keep = up ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    up = lane & 2;
+    {
+        const float send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+        w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+    return w1;
+}
+
+template <int S>
+__global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const BlendBwdParams p) {
+    __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
+    __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
+    __shared__ int s_max[BLEND_THREADS / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % p.g.tbx, tile_y = tile / p.g.tbx;
+    int lx, ly;
+    bool has_pixel;
+    tile_pixel(p.g.bw, tid, lx, ly, has_pixel);
+    const int j = tile_x * p.g.bw + lx, i = tile_y * p.g.bw + ly;
+    const bool inside = has_pixel && i < p.g.H && j < p.g.W;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const size_t pix = inside ? (size_t)i * p.g.W + j : 0;
+
+    const float roll = (float)((double)p.g.rs_time * ((double)(py / (float)p.g.H) - 0.5));
+    float tau[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        tau[s] = ((S > 1) ? ((float)s / (float)(S - 1) - 0.5f) * p.g.exposure : 0.0f) + roll;
+
+    const int2 range = p.tile_bins[tile];
+    const float inv_s = 1.0f / (float)S;
+
+    // per-pixel cotangents and per-sample state (backward.cu:198-217)
+    float vo0 = 0.f, vo1 = 0.f, vo2 = 0.f, voa = 0.f;
+    if (inside) {
+        vo0 = p.v_out[3 * pix]; vo1 = p.v_out[3 * pix + 1]; vo2 = p.v_out[3 * pix + 2];
+        voa = p.v_out_alpha[pix];
+    }
+    const float bgdot = __ldg(p.background) * vo0 + __ldg(p.background + 1) * vo1 + __ldg(p.background + 2) * vo2;
+    float T[S], Kc[S], bdot[S];
+    int bin_final[S];
+    int my_max = -1;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        T[s] = 1.f; Kc[s] = 0.f; bdot[s] = 0.f; bin_final[s] = -1;
+        if (inside) {
+            const float Tf = p.final_Ts[pix * S + s];
+            T[s] = Tf;
+            Kc[s] = Tf * inv_s * (voa - bgdot);
+            bin_final[s] = min(p.final_idx[pix * S + s], range.y - 1);  // batches only cover [range.x, range.y)
+            my_max = max(my_max, bin_final[s]);
+        }
+    }
+    const int wmax = __reduce_max_sync(0xffffffffu, my_max);  // last contributor over the warp's pixel-samples
+    if (lane == 0) s_max[warp] = wmax;
+
+    WarpWindow win;
+    {
+        const float big = 3.0e38f;
+        win.x0 = warp_min(inside ? px : big); win.x1 = warp_max(inside ? px : -big);
+        win.y0 = warp_min(inside ? py : big); win.y1 = warp_max(inside ? py : -big);
+        float tlo = big, thi = -big;
+#pragma unroll
+        for (int s = 0; s < S; ++s) { tlo = fminf(tlo, tau[s]); thi = fmaxf(thi, tau[s]); }
+        win.t0 = warp_min(inside ? tlo : big); win.t1 = warp_max(inside ? thi : -big);
+    }
+
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < BLEND_STAGES; ++st) mbar_init(&s_bar[st], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    int hi = -1;
+#pragma unroll
+    for (int w = 0; w < BLEND_THREADS / 32; ++w) hi = max(hi, s_max[w]);
+    const int total = hi - range.x + 1;  // entries hi, hi-1, ..., range.x
+    const int nb = total > 0 ? (total + BLEND_BATCH - 1) / BLEND_BATCH : 0;
+
+    // which output array / component this lane's butterfly result goes to
+    float *my_dst = nullptr;
+    int my_stride = 0;
+    {
+        const int k = lane >> 1;
+        if ((lane & 1) == 0) {
+            if (k < 3) { my_dst = p.v_rgb + k; my_stride = 3; }
+            else if (k < 6) { my_dst = p.v_conic + (k - 3); my_stride = 3; }
+            else if (k < 8) { my_dst = p.v_xy + (k - 6); my_stride = 2; }
+            else if (k < 10) { my_dst = p.v_xy_abs + (k - 8); my_stride = 2; }
+            else if (k < 12) { my_dst = p.v_pix_vel + (k - 10); my_stride = 2; }
+            else if (k == 12) { my_dst = p.v_opac; my_stride = 1; }
+        }
+    }
+
+    // stage entry t of batch b  <->  list index hi - b*BATCH - t  (t ascending = back to front)
+    auto issue = [&](int b) {
+        const int st = b & 1;
+        const int top = hi - b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, top - range.x + 1);
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], (uint32_t)cnt * (uint32_t)sizeof(PackedGaussian));
+        if (tid < cnt) {
+            const int g = __ldg(p.ids_sorted + top - tid);
+            tma_bulk_g2s(&s_rec[st][tid], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+        }
+    };
+
+    if (nb > 0) issue(0);
+    for (int b = 0; b < nb; ++b) {
+        const int st = b & 1;
+        if (b + 1 < nb) issue(b + 1);
+        mbar_wait(&s_bar[st], (uint32_t)((b >> 1) & 1));
+        const int top = hi - b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, top - range.x + 1);
+
+        if (wmax >= range.x) {
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                const int e = c0 + lane;
+                const bool keep = (e < cnt) && (top - e <= wmax) && may_touch(s_rec[st][e], win);
+                unsigned m = __ballot_sync(0xffffffffu, keep);
+                while (m) {
+                    const int k = c0 + (__ffs(m) - 1);
+                    m &= m - 1;
+                    const int idx = top - k;
+                    const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
+                    const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
+                    const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
+                    const float cut = C.w + 1e-4f;
+                    const float cdot = C.x * vo0 + C.y * vo1 + C.z * vo2;
+                    float facsum = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, gxs = 0.f, gys = 0.f, gxa = 0.f, gya = 0.f,
+                          pvx = 0.f, pvy = 0.f, vop = 0.f;
+                    bool any = false;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (idx > bin_final[s]) continue;  // backward.cu:252-254 (bin_final = -1 outside the image)
+                        const float dx = A.x + tau[s] * A.z - px;
+                        const float dy = A.y + tau[s] * A.w - py;
+                        const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
+                        if (sigma > cut || sigma < 0.f) continue;
+                        const float vis = __expf(-sigma);
+                        const float alpha = fminf(0.99f, Bq.w * vis);
+                        if (alpha < 1.f / 255.f) continue;
+                        any = true;
+                        const float ra = __frcp_rn(1.f - alpha);
+                        T[s] *= ra;
+                        const float Tm = T[s] * inv_s;
+                        const float fac = alpha * Tm;
+                        const float v_alpha = Tm * cdot + ra * (Kc[s] - bdot[s]);
+                        bdot[s] += fac * cdot;
+                        facsum += fac;
+                        const float v_sigma = -Bq.w * vis * v_alpha;
+                        sxx += v_sigma * dx * dx; sxy += v_sigma * dx * dy; syy += v_sigma * dy * dy;
+                        const float gx = v_sigma * (Bq.x * dx + Bq.y * dy);
+                        const float gy = v_sigma * (Bq.y * dx + Bq.z * dy);
+                        gxs += gx; gys += gy; gxa += fabsf(gx); gya += fabsf(gy);
+                        pvx += gx * tau[s]; pvy += gy * tau[s];
+                        vop += vis * v_alpha;
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
+                    const float v[16] = {facsum * vo0, facsum * vo1, facsum * vo2, 0.5f * sxx, sxy, 0.5f * syy,
+                                         gxs, gys, gxa, gya, pvx, pvy, vop, 0.f, 0.f, 0.f};
+                    const float tot = butterfly16(v, lane);
+                    if (my_dst && tot != 0.f) {
+                        const int gid = s_rec[st][k].id;
+                        atomicAdd(my_dst + (size_t)gid * my_stride, tot);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // stage `st` is refilled two batches from now
+    }
+}
+
+template <int S>
+static int launch_bwd(const BlendBwdParams &p, cudaStream_t st) {
+    blend_backward_kernel<S><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_rasterize_backward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                                       unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                       const int32_t *tile_bins, const float *xys, const float *pix_vels,
+                                       float rolling_shutter_time, float exposure_time, const float *conics,
+                                       const float *colors, const float *opacities, const float *background,
+                                       const float *final_Ts, const int32_t *final_idx, const float *v_output,
+                                       const float *v_output_alpha, void *packed_ws, float *v_xy, float *v_xy_abs,
+                                       float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity,
+                                       void *stream) {
+    B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");
+    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
+    B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
+    B200_REQUIRE(img_height > 0 && img_width > 0, "image size must be positive");
+    B200_REQUIRE(gaussian_ids_sorted && tile_bins && xys && pix_vels && conics && colors && opacities && background,
+                 "null input pointer");
+    B200_REQUIRE(final_Ts && final_idx && v_output && v_output_alpha, "null saved / cotangent pointer");
+    B200_REQUIRE(packed_ws && aligned16(packed_ws), "packed_ws must be a 16-byte aligned scratch buffer");
+    B200_REQUIRE(v_xy && v_xy_abs && v_pix_vels && v_conic && v_colors && v_opacity, "null output pointer");
+    cudaStream_t st = as_stream(stream);
+    const size_t n = (size_t)num_points;
+    B200_CUDA(cudaMemsetAsync(v_xy, 0, n * 2 * sizeof(float), st));
+    B200_CUDA(cudaMemsetAsync(v_xy_abs, 0, n * 2 * sizeof(float), st));
+    B200_CUDA(cudaMemsetAsync(v_pix_vels, 0, n * 2 * sizeof(float), st));
+    B200_CUDA(cudaMemsetAsync(v_conic, 0, n * 3 * sizeof(float), st));
+    B200_CUDA(cudaMemsetAsync(v_colors, 0, n * 3 * sizeof(float), st));
+    B200_CUDA(cudaMemsetAsync(v_opacity, 0, n * sizeof(float), st));
+    int rc = launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed_ws, st);
+    if (rc) return rc;
+    BlendBwdParams p;
+    p.g = BlendGeom{(int)img_height, (int)img_width, (int)block_width,
+                    (int)((img_width + block_width - 1) / block_width),
+                    (int)((img_height + block_width - 1) / block_width), rolling_shutter_time, exposure_time};
+    p.ids_sorted = gaussian_ids_sorted;
+    p.tile_bins = reinterpret_cast<const int2 *>(tile_bins);
+    p.packed = reinterpret_cast<const PackedGaussian *>(packed_ws);
+    p.background = background;
+    p.final_Ts = final_Ts; p.final_idx = final_idx; p.v_out = v_output; p.v_out_alpha = v_output_alpha;
+    p.v_xy = v_xy; p.v_xy_abs = v_xy_abs; p.v_pix_vel = v_pix_vels; p.v_conic = v_conic; p.v_rgb = v_colors;
+    p.v_opac = v_opacity;
+    switch (n_blur_samples) {
+        case 1: return launch_bwd<1>(p, st);
+        case 2: return launch_bwd<2>(p, st);
+        case 3: return launch_bwd<3>(p, st);
+        case 4: return launch_bwd<4>(p, st);
+        case 5: return launch_bwd<5>(p, st);
+        case 6: return launch_bwd<6>(p, st);
+        case 7: return launch_bwd<7>(p, st);
+        case 8: return launch_bwd<8>(p, st);
+        case 9: return launch_bwd<9>(p, st);
+        default: return launch_bwd<10>(p, st);
+    }
+}

@@ -1,0 +1,119 @@
+// Shared pieces of the blur / rolling-shutter blend kernels (blend_fwd.cu, blend_bwd.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int BLEND_THREADS = 256;  // one CTA per tile; 8 warps, each owning an 8x4 pixel sub-block at bw = 16
+constexpr int BLEND_BATCH = 256;    // tile-list entries staged per pipeline stage
+constexpr int BLEND_STAGES = 2;
+
+struct BlendGeom {
+    int H, W, bw, tbx, tby;
+    float rs_time, exposure;
+};
+
+// ---- per-Gaussian packed record -------------------------------------------------------------
+// Gathers the five per-Gaussian arrays the reference blend reads separately (forward.cu:387-394,
+// :431) into one 64-byte line and precomputes the cull data:
+//   thr      = ln(255 * opac): a pixel can only pass the reference's `alpha < 1/255` skip
+//              (forward.cu:417) if 0 <= sigma <= thr;
+//   (hx, hy) = half extents of the axis-aligned box around {sigma <= thr} (conservative, padded),
+//              +inf when the conic is not positive definite, -1 when nothing can pass (thr < 0).
+#ifdef __CUDACC__
+static __global__ void __launch_bounds__(256) pack_records_kernel(int n, const float2 *__restrict__ xys,
+                                                                  const float2 *__restrict__ pix_vels,
+                                                                  const float *__restrict__ conics,
+                                                                  const float *__restrict__ colors,
+                                                                  const float *__restrict__ opac,
+                                                                  PackedGaussian *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PackedGaussian g;
+    const float2 xy = xys[i], v = pix_vels[i];
+    g.x = xy.x; g.y = xy.y; g.vx = v.x; g.vy = v.y;
+    g.ca = conics[3 * (size_t)i]; g.cb = conics[3 * (size_t)i + 1]; g.cc = conics[3 * (size_t)i + 2];
+    g.opac = opac[i];
+    g.r = colors[3 * (size_t)i]; g.g = colors[3 * (size_t)i + 1]; g.b = colors[3 * (size_t)i + 2];
+    g.id = i;
+    g.pad = 0.f;
+    const float thr = logf(255.f * g.opac);  // opac <= 0 -> -inf / NaN
+    g.thr = thr;
+    const float det = g.ca * g.cc - g.cb * g.cb;
+    if (thr < 0.f || g.opac <= 0.f) {
+        g.hx = -1.f; g.hy = -1.f;  // alpha < 1/255 wherever sigma >= 0: can never contribute
+        g.thr = -1.f;
+    } else if (det > 0.f && g.ca > 0.f && g.cc > 0.f) {
+        const float tm = 2.f * (thr * 1.00001f + 1e-4f) / det;
+        g.hx = sqrtf(tm * g.cc) * 1.00001f + 1e-3f;
+        g.hy = sqrtf(tm * g.ca) * 1.00001f + 1e-3f;
+    } else {
+        g.hx = __int_as_float(0x7f800000); g.hy = __int_as_float(0x7f800000);  // unbounded: never culled
+    }
+    float4 *o = reinterpret_cast<float4 *>(out + i);
+    o[0] = make_float4(g.x, g.y, g.vx, g.vy);
+    o[1] = make_float4(g.ca, g.cb, g.cc, g.opac);
+    o[2] = make_float4(g.r, g.g, g.b, g.thr);
+    o[3] = make_float4(g.hx, g.hy, __int_as_float(g.id), 0.f);
+}
+
+static inline int launch_pack(int n, const float *xys, const float *pix_vels, const float *conics, const float *colors,
+                              const float *opac, void *packed_ws, cudaStream_t st) {
+    pack_records_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, reinterpret_cast<const float2 *>(xys),
+                                                          reinterpret_cast<const float2 *>(pix_vels), conics, colors,
+                                                          opac, reinterpret_cast<PackedGaussian *>(packed_ws));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("pack_records_kernel launch failed: %s", cudaGetErrorString(e));
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
+
+// thread -> pixel inside the tile.  bw == 16: warp w owns the 8x4 block (w&1, w>>1) so its pixel
+// rectangle is compact and the per-warp cull rejects most of the tile list; smaller tiles use the
+// reference's linear mapping on the first bw*bw threads.
+__device__ __forceinline__ void tile_pixel(int bw, int tid, int &lx, int &ly, bool &has_pixel) {
+    if (bw == 16) {
+        const int w = tid >> 5, lane = tid & 31;
+        lx = ((w & 1) << 3) + (lane & 7);
+        ly = ((w >> 1) << 2) + (lane >> 3);
+        has_pixel = true;
+    } else {
+        has_pixel = tid < bw * bw;
+        lx = has_pixel ? tid % bw : 0;
+        ly = has_pixel ? tid / bw : 0;
+    }
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Rectangle (pixel centres) and time window covered by the live lanes of this warp.
+struct WarpWindow {
+    float x0, x1, y0, y1, t0, t1;
+};
+
+// Conservative test: can Gaussian `g` reach alpha >= 1/255 for any pixel centre / sample time in `w`?
+// Written so that NaNs compare "keep".
+__device__ __forceinline__ bool may_touch(const PackedGaussian &g, const WarpWindow &w) {
+    const float ax = w.t0 * g.vx, bx = w.t1 * g.vx, ay = w.t0 * g.vy, by = w.t1 * g.vy;
+    const float cx0 = g.x + fminf(ax, bx), cx1 = g.x + fmaxf(ax, bx);
+    const float cy0 = g.y + fminf(ay, by), cy1 = g.y + fmaxf(ay, by);
+    const bool out = (g.hx < 0.f) || (cx0 - g.hx > w.x1) || (cx1 + g.hx < w.x0) || (cy0 - g.hy > w.y1) ||
+                     (cy1 + g.hy < w.y0);
+    return !out;
+}
+
+#endif
+
+}  // namespace b200

@@ -1,0 +1,212 @@
+// Blur / rolling-shutter alpha-blend, forward.  Semantics of
+// /root/reference/gsplat/gsplat/cuda/csrc/forward.cu:306-456.
+//
+// Differences in *how* (not what) from the reference kernel:
+//   * the tile list is walked ONCE: every staged Gaussian is evaluated for all S blur samples with the
+//     S transmittances held in registers (the reference re-stages the whole list per sample);
+//   * Gaussians are staged as one 64-byte packed record each, gathered into shared memory with
+//     per-entry TMA bulk copies (cp.async.bulk + mbarrier), double buffered against the blend;
+//   * each warp owns a compact 8x4 pixel block and first culls the staged batch against that
+//     rectangle (one Gaussian per lane + ballot), so only Gaussians that can reach alpha >= 1/255
+//     somewhere in the warp's pixels / sample times are evaluated.  The cull is conservative and the
+//     exact per-pixel tests of the reference are kept, so results do not change.
+// Bound: FP32 issue + MUFU.EX2 (hundreds of flop per staged byte), not HBM -- see DESIGN.md.
+#include "blend_common.cuh"
+
+namespace b200 {
+
+struct BlendFwdParams {
+    BlendGeom g;
+    const int32_t *ids_sorted;
+    const int2 *tile_bins;
+    const PackedGaussian *packed;
+    const float *background;  // device float[3]
+    float *out_img;           // (H,W,3)
+    float *final_Ts;          // (H,W,S)
+    int32_t *final_idx;       // (H,W,S)
+};
+
+template <int S>
+__global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const BlendFwdParams p) {
+    __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
+    __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % p.g.tbx, tile_y = tile / p.g.tbx;
+    int lx, ly;
+    bool has_pixel;
+    tile_pixel(p.g.bw, tid, lx, ly, has_pixel);
+    const int j = tile_x * p.g.bw + lx, i = tile_y * p.g.bw + ly;
+    const bool inside = has_pixel && i < p.g.H && j < p.g.W;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+
+    // per-sample time offsets: blur_rel of forward.cu:360-363
+    const float roll = (float)((double)p.g.rs_time * ((double)(py / (float)p.g.H) - 0.5));
+    float tau[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        tau[s] = ((S > 1) ? ((float)s / (float)(S - 1) - 0.5f) * p.g.exposure : 0.0f) + roll;
+
+    // the warp's pixel rectangle and time window (live lanes only)
+    WarpWindow win;
+    {
+        const float big = 3.0e38f;
+        win.x0 = warp_min(inside ? px : big); win.x1 = warp_max(inside ? px : -big);
+        win.y0 = warp_min(inside ? py : big); win.y1 = warp_max(inside ? py : -big);
+        float tlo = big, thi = -big;
+#pragma unroll
+        for (int s = 0; s < S; ++s) { tlo = fminf(tlo, tau[s]); thi = fmaxf(thi, tau[s]); }
+        win.t0 = warp_min(inside ? tlo : big); win.t1 = warp_max(inside ? thi : -big);
+    }
+
+    const int2 range = p.tile_bins[tile];
+    const int total = range.y - range.x;
+    const int nb = (total + BLEND_BATCH - 1) / BLEND_BATCH;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < BLEND_STAGES; ++st) mbar_init(&s_bar[st], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int b) {
+        const int st = b & 1;
+        const int start = range.x + b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, range.y - start);
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], (uint32_t)cnt * (uint32_t)sizeof(PackedGaussian));
+        if (tid < cnt) {
+            const int g = __ldg(p.ids_sorted + start + tid);
+            tma_bulk_g2s(&s_rec[st][tid], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+        }
+    };
+
+    float T[S];
+    int last[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { T[s] = 1.f; last[s] = 0; }
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+    unsigned alive = inside ? ((1u << S) - 1u) : 0u;
+    const float inv_s = 1.0f / (float)S;
+
+    int b = 0;
+    bool pending = false;
+    if (nb > 0) { issue(0); pending = true; }
+    for (; b < nb; ++b) {
+        const int st = b & 1;
+        if (b + 1 < nb) issue(b + 1);
+        mbar_wait(&s_bar[st], (uint32_t)((b >> 1) & 1));
+        pending = (b + 1 < nb);
+        const int start = range.x + b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, range.y - start);
+
+        if (__any_sync(0xffffffffu, alive != 0u)) {
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                const int e = c0 + lane;
+                const bool keep = (e < cnt) && may_touch(s_rec[st][e], win);
+                unsigned m = __ballot_sync(0xffffffffu, keep);
+                while (m) {
+                    const int k = c0 + (__ffs(m) - 1);
+                    m &= m - 1;
+                    const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
+                    const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
+                    const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
+                    const float cut = C.w + 1e-4f;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (!(alive & (1u << s))) continue;
+                        const float dx = A.x + tau[s] * A.z - px;
+                        const float dy = A.y + tau[s] * A.w - py;
+                        const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
+                        if (sigma > cut || sigma < 0.f) continue;  // alpha < 1/255 guaranteed above thr
+                        const float alpha = fminf(0.999f, Bq.w * __expf(-sigma));
+                        if (alpha < 1.f / 255.f) continue;
+                        const float next_T = T[s] * (1.f - alpha);
+                        if (next_T <= 1e-4f) {  // forward.cu:421-427: this sample is done, entry not blended
+                            alive &= ~(1u << s);
+                            continue;
+                        }
+                        const float vis = alpha * T[s] * inv_s;
+                        acc_r += C.x * vis; acc_g += C.y * vis; acc_b += C.z * vis;
+                        T[s] = next_T;
+                        last[s] = start + k;
+                    }
+                    if (!__any_sync(0xffffffffu, alive != 0u)) { m = 0; c0 = cnt; }
+                }
+            }
+        }
+        // all warps are done with stage `st` (it is refilled two batches from now) + early exit vote
+        if (!__syncthreads_or(alive != 0u)) { ++b; break; }
+    }
+    if (pending && b < nb) mbar_wait(&s_bar[b & 1], (uint32_t)((b >> 1) & 1));  // drain the prefetch before exit
+
+    if (inside) {
+        const size_t pix = (size_t)i * p.g.W + j;
+        float meanT = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            meanT += T[s] * inv_s;
+            p.final_Ts[pix * S + s] = T[s];
+            p.final_idx[pix * S + s] = last[s];
+        }
+        const float bg0 = __ldg(p.background), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
+        p.out_img[3 * pix] = acc_r + meanT * bg0;
+        p.out_img[3 * pix + 1] = acc_g + meanT * bg1;
+        p.out_img[3 * pix + 2] = acc_b + meanT * bg2;
+    }
+}
+
+template <int S>
+static int launch_fwd(const BlendFwdParams &p, cudaStream_t st) {
+    blend_forward_kernel<S><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" size_t b200_packed_record_bytes(void) { return sizeof(PackedGaussian); }
+
+extern "C" int b200_rasterize_forward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                                      unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                      const int32_t *tile_bins, const float *xys, const float *pix_vels,
+                                      float rolling_shutter_time, float exposure_time, const float *conics,
+                                      const float *colors, const float *opacities, const float *background,
+                                      void *packed_ws, float *out_img, float *final_Ts, int32_t *final_idx,
+                                      void *stream) {
+    B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");  // bindings.cu:450-452
+    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
+    B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
+    B200_REQUIRE(img_height > 0 && img_width > 0, "image size must be positive");
+    B200_REQUIRE(gaussian_ids_sorted && tile_bins && xys && pix_vels && conics && colors && opacities && background,
+                 "null input pointer");
+    B200_REQUIRE(packed_ws && aligned16(packed_ws), "packed_ws must be a 16-byte aligned scratch buffer");
+    B200_REQUIRE(out_img && final_Ts && final_idx, "null output pointer");
+    cudaStream_t st = as_stream(stream);
+    int rc = launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed_ws, st);
+    if (rc) return rc;
+    BlendFwdParams p;
+    p.g = BlendGeom{(int)img_height, (int)img_width, (int)block_width,
+                    (int)((img_width + block_width - 1) / block_width),
+                    (int)((img_height + block_width - 1) / block_width), rolling_shutter_time, exposure_time};
+    p.ids_sorted = gaussian_ids_sorted;
+    p.tile_bins = reinterpret_cast<const int2 *>(tile_bins);
+    p.packed = reinterpret_cast<const PackedGaussian *>(packed_ws);
+    p.background = background;
+    p.out_img = out_img; p.final_Ts = final_Ts; p.final_idx = final_idx;
+    switch (n_blur_samples) {
+        case 1: return launch_fwd<1>(p, st);
+        case 2: return launch_fwd<2>(p, st);
+        case 3: return launch_fwd<3>(p, st);
+        case 4: return launch_fwd<4>(p, st);
+        case 5: return launch_fwd<5>(p, st);
+        case 6: return launch_fwd<6>(p, st);
+        case 7: return launch_fwd<7>(p, st);
+        case 8: return launch_fwd<8>(p, st);
+        case 9: return launch_fwd<9>(p, st);
+        default: return launch_fwd<10>(p, st);
+    }
+}

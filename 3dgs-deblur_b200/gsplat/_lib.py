@@ -1,0 +1,88 @@
+"""ctypes loader for libb200splat.so (C ABI declared in include/b200splat.h).
+
+The library is built in-tree by `3dgs-deblur_b200/build.py` (or `__graft_entry__.build()`).  There is
+no CPU / PyTorch fallback: if the library is missing every operator raises, loudly.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200splat.so")
+
+_p, _i, _u, _f, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/b200splat.h one to one
+SIGNATURES = {
+    "b200_abi_version": (_i, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_packed_record_bytes": (_sz, []),
+    "b200_project_gaussians_forward": (_i, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _p, _f, _f, _f, _f, _u, _u, _u, _f,
+                                            _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_project_gaussians_backward": (_i, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _p, _f, _f, _f, _f, _u, _u,
+                                             _p, _p, _p, _p, _p, _p, _p, _p, _p, _u,
+                                             _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_compute_cov2d_bounds": (_i, [_i, _p, _p, _p, _p]),
+    "b200_compute_sh_forward": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
+    "b200_compute_sh_backward": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
+    "b200_scan_temp_bytes": (_sz, [_i]),
+    "b200_cumulative_intersects": (_i, [_i, _p, _p, _p, _sz, _p, _p]),
+    "b200_map_gaussian_to_intersects": (_i, [_i, _i, _p, _p, _p, _p, _u, _u, _u, _p, _p, _p]),
+    "b200_sort_temp_bytes": (_sz, [_i]),
+    "b200_sort_intersects": (_i, [_i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "b200_get_tile_bin_edges": (_i, [_i, _i, _p, _p, _p]),
+    "b200_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
+                                     _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_nd_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_nd_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                        _p, _p, _p, _p, _p, _p]),
+}
+
+_LIB = None
+
+
+def load():
+    """dlopen the library once and attach prototypes.  Raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libb200splat.so not found at {LIB_PATH}. Build it with "
+                "`python 3dgs-deblur_b200/build.py` (needs nvcc); there is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.b200_abi_version() != 1:
+            raise RuntimeError("libb200splat.so ABI version mismatch; rebuild it")
+        _LIB = lib
+    return _LIB
+
+
+def check(rc):
+    """0 -> ok; otherwise raise like the reference's TORCH_CHECK / AT_ERROR (RuntimeError)."""
+    if rc != 0:
+        raise RuntimeError(load().b200_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    """The reference's CHECK_INPUT (bindings.h:10-15): CUDA + contiguous, else RuntimeError."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("tensor must be a CUDA tensor (libb200splat has no CPU path)")
+        if not t.is_contiguous():
+            raise RuntimeError("tensor must be contiguous")

@@ -1,0 +1,168 @@
+/*
+ * b200splat.h -- C ABI of libb200splat.so: the B200 (sm_100a) rasterizer hot path.
+ *
+ * This is the drop-in boundary below the gsplat Python operators.  Each entry point
+ * replaces one function of the reference's pybind/libtorch module
+ * (/root/reference/gsplat/gsplat/cuda/csrc/ext.cpp:4-18, declared in bindings.h:19-225);
+ * the reference interface it replaces is cited per function.
+ *
+ * Conventions (all functions):
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless
+ *     marked "host"; outputs are caller-allocated and need NOT be zero-initialised
+ *     (the kernels write every element, including the zeros the reference obtains
+ *     from its torch::zeros allocations);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) of the CURRENT device and the call returns without synchronising;
+ *   - return value 0 = success, negative = error (B200_ERR_*); b200_last_error()
+ *     gives a thread-local message.  No exceptions cross the boundary; reentrant.
+ *   - float = IEEE fp32, ids/offsets int32, sort keys int64 -- as in the reference.
+ */
+#ifndef B200SPLAT_H
+#define B200SPLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#define B200_ABI_VERSION 1
+#define B200_MAX_BLUR_SAMPLES 10 /* helpers.cuh:222 */
+#define B200_OK 0
+#define B200_ERR_INVALID (-1) /* bad argument (the reference raises TORCH_CHECK / AT_ERROR) */
+#define B200_ERR_CUDA (-2)    /* a CUDA runtime call or launch failed */
+
+#define B200_SH_POLY 0 /* sh.cuh:268-340 */
+#define B200_SH_FAST 1 /* sh.cuh:54-156  */
+
+/* project_gaussians_backward flags */
+#define B200_PROJ_EXACT 1u /* clamp-aware J and full dL/dviewmat: the gradients of the reference's
+                              torch path (project_gaussians.py:81-112); 0 = reference CUDA path
+                              (backward.cu:454-532 ignores the fov clamp; project_gaussians.py:272-307
+                              approximates dL/dR) */
+
+B200_API int b200_abi_version(void);
+B200_API const char *b200_last_error(void);
+
+/* Size of one packed per-Gaussian blend record (bytes); scratch for the blend = N * this. */
+B200_API size_t b200_packed_record_bytes(void);
+
+/* ---- projection ------------------------------------------------------------------------
+ * replaces project_gaussians_forward_tensor (bindings.h:43-72, bindings.cu:154-257; kernel
+ * forward.cu:13-112).  lin_vel / ang_vel are DEVICE float[3] (NULL = zero) so the caller never
+ * needs the .tolist() D2H sync of project_gaussians.py:178-179.  viewmat: >= 12 floats row-major.
+ * Outputs: cov3d (N,6) xys (N,2) depths (N) pix_vels (N,2) radii (N) i32 conics (N,3)
+ * compensation (N) num_tiles_hit (N) i32. */
+B200_API int b200_project_gaussians_forward(int num_points, const float *means3d, const float *scales, float glob_scale,
+                                   const float *quats, const float *lin_vel, const float *ang_vel,
+                                   float rolling_shutter_time, float exposure_time, const float *viewmat, float fx,
+                                   float fy, float cx, float cy, unsigned img_height, unsigned img_width,
+                                   unsigned block_width, float clip_thresh, float *cov3d, float *xys, float *depths,
+                                   float *pix_vels, int32_t *radii, float *conics, float *compensation,
+                                   int32_t *num_tiles_hit, void *stream);
+
+/* replaces project_gaussians_backward_tensor (bindings.h:74-108, bindings.cu:259-358; kernel
+ * backward.cu:371-451) AND the Python-side v_viewmat block (project_gaussians.py:272-307) AND adds
+ * the camera-velocity gradients the reference only has through its torch path.
+ * v_cov2d (N,3) / v_cov3d (N,6) are optional scratch outputs (NULL = not materialised).
+ * v_mean3d (N,3) v_scale (N,3) v_quat (N,4) are written for every Gaussian (zeros where radii<=0).
+ * v_lin_vel[3], v_ang_vel[3], v_viewmat[12] are optional; when non-NULL they are OVERWRITTEN with
+ * the sums over Gaussians (block-reduced in the kernel, one atomic per block and component). */
+B200_API int b200_project_gaussians_backward(int num_points, const float *means3d, const float *scales, float glob_scale,
+                                    const float *quats, const float *lin_vel, const float *ang_vel,
+                                    float rolling_shutter_time, float exposure_time, const float *viewmat, float fx,
+                                    float fy, float cx, float cy, unsigned img_height, unsigned img_width,
+                                    const float *cov3d, const int32_t *radii, const float *conics,
+                                    const float *compensation, const float *v_xy, const float *v_depth,
+                                    const float *v_pix_vel, const float *v_conic, const float *v_compensation,
+                                    unsigned flags, float *v_cov2d, float *v_cov3d, float *v_mean3d, float *v_scale,
+                                    float *v_quat, float *v_lin_vel, float *v_ang_vel, float *v_viewmat,
+                                    void *stream);
+
+/* replaces compute_cov2d_bounds_tensor (bindings.h:19-22, bindings.cu:19-60): conics (N,3), radii (N) f32 */
+B200_API int b200_compute_cov2d_bounds(int num_pts, const float *cov2d, float *conics, float *radii, void *stream);
+
+/* ---- spherical harmonics ----------------------------------------------------------------
+ * replaces compute_sh_forward_tensor / compute_sh_backward_tensor (bindings.h:24-41,
+ * bindings.cu:62-151; kernels sh.cuh:434-498).  coeffs (N,K,3), K = (degree+1)^2, 3 channels;
+ * viewdirs (N,3) un-normalised; v_coeffs rows >= (degrees_to_use+1)^2 are written as zeros. */
+B200_API int b200_compute_sh_forward(int method, int num_points, int degree, int degrees_to_use, const float *viewdirs,
+                            const float *coeffs, float *colors, void *stream);
+B200_API int b200_compute_sh_backward(int method, int num_points, int degree, int degrees_to_use, const float *viewdirs,
+                             const float *v_colors, float *v_coeffs, void *stream);
+
+/* ---- tile binning -----------------------------------------------------------------------
+ * b200_cumulative_intersects replaces torch.cumsum in compute_cumulative_intersects
+ * (gsplat/utils.py:106-125): inclusive int32 scan.  `total_host_pinned` (HOST, optional) receives
+ * cum[N-1] by an async copy on `stream` (the caller synchronises before reading it). */
+B200_API size_t b200_scan_temp_bytes(int num_points);
+B200_API int b200_cumulative_intersects(int num_points, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit, void *temp,
+                               size_t temp_bytes, int32_t *total_host_pinned, void *stream);
+
+/* replaces map_gaussian_to_intersects_tensor (bindings.h:199-209, bindings.cu:360-402; kernel
+ * forward.cu:116-153).  Slots reserved by cum_tiles_hit but not emitted (the reference's "phantom"
+ * entries, which keep their zeros init) are written as key 0 / id 0 here too. */
+B200_API int b200_map_gaussian_to_intersects(int num_points, int num_intersects, const float *xys, const float *depths,
+                                    const int32_t *radii, const int32_t *cum_tiles_hit, unsigned tiles_x,
+                                    unsigned tiles_y, unsigned block_width, int64_t *isect_ids,
+                                    int32_t *gaussian_ids, void *stream);
+
+/* replaces torch.sort + torch.gather in bin_and_sort_gaussians (gsplat/utils.py:179-180): stable LSD
+ * radix sort of (key, id) pairs on the bits that can be set (32 depth bits + ceil(log2(num_tiles))). */
+B200_API size_t b200_sort_temp_bytes(int num_intersects);
+B200_API int b200_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids, const int32_t *gaussian_ids,
+                         int64_t *isect_ids_sorted, int32_t *gaussian_ids_sorted, void *temp, size_t temp_bytes,
+                         void *stream);
+
+/* replaces get_tile_bin_edges_tensor (bindings.h:211-215, bindings.cu:404-422; kernel forward.cu:158-180):
+ * tile_bins (num_tiles,2) i32, (0,0) for empty tiles. */
+B200_API int b200_get_tile_bin_edges(int num_intersects, int num_tiles, const int64_t *isect_ids_sorted, int32_t *tile_bins,
+                            void *stream);
+
+/* ---- blend (blur + rolling shutter), 3 channels ------------------------------------------
+ * replaces rasterize_forward_tensor (bindings.h:110-127, bindings.cu:424-503; kernel forward.cu:306-456).
+ * packed_ws: scratch of num_points * b200_packed_record_bytes() bytes, 16-byte aligned (filled here).
+ * out_img (H,W,3), final_Ts (H,W,S) f32, final_idx (H,W,S) i32.  background: DEVICE float[3]. */
+B200_API int b200_rasterize_forward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                           unsigned n_blur_samples, const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                           const float *xys, const float *pix_vels, float rolling_shutter_time, float exposure_time,
+                           const float *conics, const float *colors, const float *opacities, const float *background,
+                           void *packed_ws, float *out_img, float *final_Ts, int32_t *final_idx, void *stream);
+
+/* replaces rasterize_backward_tensor (bindings.h:168-197, bindings.cu:684-773; kernel backward.cu:143-369).
+ * v_xy, v_xy_abs, v_pix_vels (N,2); v_conic, v_colors (N,3); v_opacity (N): overwritten (zeroed inside).
+ * packed_ws as above (re-filled here, so forward and backward may use different scratch). */
+B200_API int b200_rasterize_backward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                            unsigned n_blur_samples, const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                            const float *xys, const float *pix_vels, float rolling_shutter_time, float exposure_time,
+                            const float *conics, const float *colors, const float *opacities, const float *background,
+                            const float *final_Ts, const int32_t *final_idx, const float *v_output,
+                            const float *v_output_alpha, void *packed_ws, float *v_xy, float *v_xy_abs,
+                            float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity, void *stream);
+
+/* ---- N-channel blend (no blur), fp16 accumulators like the reference ----------------------
+ * replaces nd_rasterize_forward_tensor / nd_rasterize_backward_tensor (bindings.h:129-166,
+ * bindings.cu:506-682; kernels forward.cu:185-304, backward.cu:22-141). */
+B200_API int b200_nd_rasterize_forward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                              unsigned channels, const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                              const float *xys, const float *conics, const float *colors, const float *opacities,
+                              const float *background, float *out_img, float *final_Ts, int32_t *final_idx,
+                              void *stream);
+B200_API int b200_nd_rasterize_backward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                               unsigned channels, const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                               const float *xys, const float *conics, const float *colors, const float *opacities,
+                               const float *background, const float *final_Ts, const int32_t *final_idx,
+                               const float *v_output, const float *v_output_alpha, float *v_xy, float *v_xy_abs,
+                               float *v_conic, float *v_colors, float *v_opacity, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPLAT_H */

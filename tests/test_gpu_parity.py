@@ -1,0 +1,424 @@
+"""GPU parity: libb200splat (through the gsplat operator surface / C ABI) vs the CPU oracle.
+
+Tolerances (fp32 path; the reference's own tests use atol=rtol=1e-5 forward, 5e-4 backward,
+gsplat/tests/test_project_gaussians.py:129-136,:319-325):
+  * integer / ordering outputs (radii, num_tiles_hit, isect ids, sorted ids, tile bins, final_idx): exact;
+    where a float rounding can flip a ceil()/threshold (radius, last-contributor index) at most 1e-4 of the
+    entries may differ on the large cases and none on the reference-sized ones.
+  * projection floats: 1e-5 relative (+2e-4 px absolute for pixel coordinates);
+  * image: atol 2e-5 (PSNR-equivalent > 90 dB vs the oracle); final_Ts atol 1e-6 rel 1e-5;
+  * gradients: 1e-3 of the largest magnitude of each tensor (fp32 atomics vs fp64 oracle sums).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import gsplat
+    import gsplat.cuda as _C
+    from gsplat import project_gaussians, rasterize_gaussians, spherical_harmonics
+
+from oracle import oracle as O
+from oracle import torch_oracle as TO
+from util_scene import cu, frac_mismatch, oracle_colors, oracle_project, oracle_render, scene_np
+
+
+def close(a, b, atol, rtol, name=""):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert (err <= 0).all(), f"{name}: {int((err > 0).sum())} / {err.size} out of tol, max abs diff {np.abs(a - b).max():.3e}"
+
+
+def grad_close(a, b, tol=1e-3, name=""):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = np.asarray(b, np.float64)
+    scale = max(np.abs(b).max(), 1e-12)
+    err = np.abs(a.astype(np.float64) - b).max() / scale
+    assert err <= tol, f"{name}: max err {err:.3e} of max |ref| {scale:.3e}"
+
+
+def gpu_project(d, lin=None, ang=None, viewmat=None, means=None, scales=None, quats=None):
+    return project_gaussians(
+        cu(d["means"]) if means is None else means, cu(d["scales"]) if scales is None else scales, 1.0,
+        cu(d["quats"]) if quats is None else quats, cu(d["lin_vel"]) if lin is None else lin,
+        cu(d["ang_vel"]) if ang is None else ang, d["rs"], d["exposure"],
+        cu(d["viewmat"]) if viewmat is None else viewmat, d["fx"], d["fy"], d["cx"], d["cy"], d["H"], d["W"], d["bw"])
+
+
+PROJ_CASES = [("c1", None, False, 0.0), ("c2", 20000, True, 1e-4), ("c2", None, True, 1e-4), ("c4", 50000, True, 1e-4)]
+
+
+@pytest.mark.parametrize("name,n,motion,int_tol", PROJ_CASES)
+def test_projection_forward_vs_oracle(name, n, motion, int_tol):
+    d = scene_np(name, n=n, motion=motion)
+    o = oracle_project(d)
+    xys, depths, pix_vels, radii, conics, comp, nth, cov3d = gpu_project(d)
+    assert frac_mismatch(radii.cpu().numpy(), o["radii"]) <= int_tol
+    assert frac_mismatch(nth.cpu().numpy(), o["num_tiles_hit"]) <= int_tol
+    m = (nth.cpu().numpy() > 0) & (o["num_tiles_hit"] > 0)
+    assert m.sum() > 100
+    close(cov3d.cpu().numpy()[m], o["cov3d"][m], 1e-7, 1e-5, "cov3d")
+    close(xys.cpu().numpy()[m], o["xys"][m], 2e-4, 1e-5, "xys")
+    close(depths.cpu().numpy()[m], o["depths"][m], 1e-6, 1e-5, "depths")
+    close(conics.cpu().numpy()[m], o["conics"][m], 1e-6, 1e-4, "conics")
+    close(comp.cpu().numpy()[m], o["compensation"][m], 1e-5, 1e-5, "compensation")
+    close(pix_vels.cpu().numpy()[m], o["pix_vels"][m], 1e-3, 1e-4, "pix_vels")
+    # culled Gaussians: every output the reference leaves at its zeros init is zero here too
+    c = o["num_tiles_hit"] == 0
+    assert (xys.cpu().numpy()[c] == o["xys"][c]).all() and (depths.cpu().numpy()[c] == 0).all()
+    close(conics.cpu().numpy()[c], o["conics"][c], 1e-6, 1e-4, "conics of culled (written before the bbox cull)")
+
+
+def test_projection_forward_reference_test_case(golden):
+    """The reference's own test inputs (seed 42, N=100, 512^2, rs=0.1, exposure=0.2) at its tolerances."""
+    for case in ("proj_seed42.npz", "proj_seed42_static.npz"):
+        g = golden(case)
+        out = project_gaussians(cu(g["means"]), cu(g["scales"]), float(g["glob_scale"]), cu(g["quats"]),
+                                cu(g["lin_vel"]), cu(g["ang_vel"]), float(g["rs_time"]), float(g["exposure"]),
+                                cu(g["viewmat"]), float(g["fx"]), float(g["fy"]), float(g["cx"]), float(g["cy"]),
+                                int(g["H"]), int(g["W"]), 16, 0.01)
+        xys, depths, pix_vels, radii, conics, comp, nth, cov3d = [t.cpu().numpy() for t in out]
+        m = g["mask"]
+        assert ((nth > 0) == m).all()
+        assert (radii[m] == g["radii"][m]).all() and (nth[m] == g["num_tiles_hit"][m]).all()
+        close(cov3d[m], g["cov3d"][m], 1e-5, 1e-5, "cov3d")
+        close(xys[m], g["xys"][m], 2e-4, 1e-5, "xys")
+        close(depths[m], g["depths"][m], 1e-5, 1e-5, "depths")
+        close(conics[m], g["conics"][m], 1e-5, 1e-4, "conics")
+        close(comp[m], g["compensation"][m], 1e-5, 1e-5, "comp")
+        close(pix_vels[m], g["pix_vels"][m], 1e-3, 1e-4, "pix_vels")
+
+
+def _cotangents(n, mask, seed):
+    g = np.random.default_rng(seed)
+    mk = mask.astype(np.float32)
+    return dict(v_xys=(g.standard_normal((n, 2)) * mk[:, None]).astype(np.float32),
+                v_depths=(g.standard_normal(n) * mk).astype(np.float32),
+                v_pix_vels=(g.standard_normal((n, 2)) * 0.01 * mk[:, None]).astype(np.float32),
+                v_conics=(g.standard_normal((n, 3)) * mk[:, None]).astype(np.float32),
+                v_compensation=(g.standard_normal(n) * mk).astype(np.float32))
+
+
+@pytest.mark.parametrize("name,n", [("c2", 20000), ("c4", 30000)])
+def test_projection_backward_cuda_path_vs_c_oracle(name, n):
+    """Velocities without grad -> the reference's CUDA backward (backward.cu:371-572) + its approximate
+    viewmat gradient (project_gaussians.py:272-307)."""
+    d = scene_np(name, n=n)
+    o = oracle_project(d)
+    ct = _cotangents(d["N"], o["num_tiles_hit"] > 0, 3)
+    means = cu(d["means"]).requires_grad_(True)
+    scales = cu(d["scales"]).requires_grad_(True)
+    quats = cu(d["quats"]).requires_grad_(True)
+    vm = cu(d["viewmat"]).requires_grad_(True)
+    xys, depths, pix_vels, radii, conics, comp, nth, cov3d = gpu_project(d, viewmat=vm, means=means, scales=scales, quats=quats)
+    loss = ((xys * cu(ct["v_xys"])).sum() + (depths * cu(ct["v_depths"])).sum() + (pix_vels * cu(ct["v_pix_vels"])).sum()
+            + (conics * cu(ct["v_conics"])).sum() + (comp * cu(ct["v_compensation"])).sum())
+    loss.backward()
+    b = O.project_backward(d["means"], d["scales"], 1.0, d["quats"], d["lin_vel"], d["ang_vel"], d["rs"], d["exposure"],
+                           d["viewmat"], d["fx"], d["fy"], o["cov3d"], o["radii"], o["conics"], o["compensation"],
+                           ct["v_xys"], ct["v_depths"], ct["v_pix_vels"], ct["v_conics"], ct["v_compensation"])
+    same = (radii.cpu().numpy() > 0) == (o["radii"] > 0)
+    grad_close(means.grad.cpu().numpy()[same], b["v_mean3d"][same], 2e-3, "v_mean3d")
+    grad_close(scales.grad.cpu().numpy()[same], b["v_scale"][same], 2e-3, "v_scale")
+    grad_close(quats.grad.cpu().numpy()[same], b["v_quat"][same], 2e-3, "v_quat")
+    # approximate viewmat gradient of the CUDA path: v_cam = v_mean R^T ; t: sum ; R[j,l] = sum v_cam[j] mean[l]
+    R = d["viewmat"][:3, :3].astype(np.float64)
+    v_cam = b["v_mean3d"].astype(np.float64) @ R.T
+    ref_vm = np.concatenate([v_cam.T @ d["means"].astype(np.float64), v_cam.sum(0)[:, None]], 1)
+    grad_close(vm.grad, ref_vm, 5e-3, "v_viewmat (approx)")
+
+
+@pytest.mark.parametrize("name,n", [("c2", 20000), ("c4", 30000)])
+def test_projection_backward_exact_path_vs_fp64_autograd(name, n):
+    """Velocities with grad -> gradients of the reference's torch path incl. velocity / exact viewmat grads."""
+    d = scene_np(name, n=n)
+    o = oracle_project(d)
+    ct = _cotangents(d["N"], o["num_tiles_hit"] > 0, 4)
+    leaves = dict(means=cu(d["means"]), scales=cu(d["scales"]), quats=cu(d["quats"]), lin=cu(d["lin_vel"]),
+                  ang=cu(d["ang_vel"]), vm=cu(d["viewmat"]))
+    for v in leaves.values():
+        v.requires_grad_(True)
+    xys, depths, pix_vels, radii, conics, comp, nth, cov3d = gpu_project(
+        d, lin=leaves["lin"], ang=leaves["ang"], viewmat=leaves["vm"], means=leaves["means"], scales=leaves["scales"],
+        quats=leaves["quats"])
+    # only send gradient where both sides rasterise the Gaussian (the torch bbox keeps a few more: see DESIGN quirks)
+    vm4 = np.concatenate([d["viewmat"], np.array([[0, 0, 0, 1.0]], np.float32)], 0)
+    t64 = lambda a: torch.from_numpy(np.asarray(a)).double()
+    inputs = dict(means=t64(d["means"]), scales=t64(d["scales"]), quats=t64(d["quats"]), lin_vel=t64(d["lin_vel"]),
+                  ang_vel=t64(d["ang_vel"]), viewmat=t64(vm4))
+    cfg = dict(glob_scale=1.0, rs_time=d["rs"], exposure=d["exposure"], fx=d["fx"], fy=d["fy"], cx=d["cx"], cy=d["cy"],
+               H=d["H"], W=d["W"], block_width=16)
+    with torch.no_grad():
+        mask64 = TO.project(inputs["means"], inputs["scales"], 1.0, inputs["quats"], inputs["lin_vel"],
+                            inputs["ang_vel"], d["rs"], d["exposure"], inputs["viewmat"], d["fx"], d["fy"], d["cx"],
+                            d["cy"], d["H"], d["W"], 16)["mask"].numpy()
+    both = mask64 & (radii.cpu().numpy() > 0)
+    ct = {k: v * (both[:, None] if v.ndim == 2 else both) for k, v in ct.items()}
+    loss = ((xys * cu(ct["v_xys"])).sum() + (depths * cu(ct["v_depths"])).sum() + (pix_vels * cu(ct["v_pix_vels"])).sum()
+            + (conics * cu(ct["v_conics"])).sum() + (comp * cu(ct["v_compensation"])).sum())
+    loss.backward()
+    grads, _ = TO.project_vjp(inputs, {k: t64(v) for k, v in ct.items()}, **cfg)
+    grad_close(leaves["means"].grad, grads["v_means"].numpy(), 2e-3, "v_means")
+    grad_close(leaves["scales"].grad, grads["v_scales"].numpy(), 2e-3, "v_scales")
+    grad_close(leaves["quats"].grad, grads["v_quats"].numpy(), 2e-3, "v_quats")
+    grad_close(leaves["lin"].grad, grads["v_lin_vel"].numpy(), 2e-3, "v_lin_vel")
+    grad_close(leaves["ang"].grad, grads["v_ang_vel"].numpy(), 2e-3, "v_ang_vel")
+    grad_close(leaves["vm"].grad, grads["v_viewmat"].numpy()[:3], 2e-3, "v_viewmat (exact)")
+
+
+@pytest.mark.parametrize("method", ["poly", "fast"])
+@pytest.mark.parametrize("k,deg_use", [(25, 4), (16, 3), (16, 1), (9, 2), (4, 0), (1, 0)])
+def test_sh_forward_backward_vs_oracle(method, k, deg_use):
+    g = np.random.default_rng(k * 10 + deg_use)
+    n = 5000 + 37
+    dirs = g.standard_normal((n, 3)).astype(np.float32)
+    coeffs = g.standard_normal((n, k, 3)).astype(np.float32)
+    v = g.standard_normal((n, 3)).astype(np.float32)
+    c = cu(coeffs).requires_grad_(True)
+    col = spherical_harmonics(deg_use, cu(dirs), c, method)
+    close(col, O.sh_forward(method, deg_use, dirs, coeffs), 2e-6, 1e-5, "sh colors")
+    col.backward(cu(v))
+    deg = {1: 0, 4: 1, 9: 2, 16: 3, 25: 4}[k]
+    close(c.grad, O.sh_backward(method, deg, deg_use, dirs, v), 1e-6, 1e-5, "sh v_coeffs")
+
+
+def test_sh_golden_reference(golden):
+    g = golden("sh.npz")
+    for method in ("poly", "fast"):
+        for deg in range(5):
+            col = spherical_harmonics(deg, cu(g["dirs"]), cu(g["coeffs"]), method)
+            close(col, g[f"{method}_{deg}"], 2e-5, 1e-5, f"sh golden {method} {deg}")
+
+
+@pytest.mark.parametrize("name,n,motion", [("c1", None, False), ("c2", 30000, True), ("c2", None, True)])
+def test_binning_bit_exact_vs_oracle(name, n, motion):
+    """Keys, stable sort order (ties by Gaussian id), tile ranges and the phantom zero-key slots: exact."""
+    d = scene_np(name, n=n, motion=motion)
+    o = oracle_project(d)
+    b = O.bin_and_sort(o["xys"], o["depths"], o["radii"], o["num_tiles_hit"], d["H"], d["W"], d["bw"])
+    tb = ((d["W"] + 15) // 16, (d["H"] + 15) // 16, 1)
+    m, cum = gsplat.compute_cumulative_intersects(cu(o["num_tiles_hit"]))
+    assert m == b["num_intersects"] and np.array_equal(cum.cpu().numpy(), b["cum_tiles_hit"])
+    out = gsplat.bin_and_sort_gaussians(d["N"], m, cu(o["xys"]), cu(o["depths"]), cu(o["radii"]), cum, tb, 16)
+    names = ["isect_ids", "gaussian_ids", "isect_ids_sorted", "gaussian_ids_sorted", "tile_bins"]
+    for t, k in zip(out, names):
+        assert np.array_equal(t.cpu().numpy(), b[k]), k
+    if motion:
+        assert (b["isect_ids"] == 0).sum() > 0  # the blur-inflated float radius really produces phantom slots
+
+
+def test_map_and_bins_golden_reference(golden):
+    g = golden("map_bins.npz")
+    H, W, bw = int(g["H"]), int(g["W"]), int(g["bw"])
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    m, cum = gsplat.compute_cumulative_intersects(cu(g["num_tiles_hit"]))
+    out = gsplat.bin_and_sort_gaussians(300, m, cu(g["xys"]), cu(g["depths"]), cu(g["radii"]), cum, tb, bw)
+    for t, k in zip(out, ["isect_ids", "gaussian_ids", "isect_ids_sorted", "gaussian_ids_sorted", "tile_bins"]):
+        assert np.array_equal(t.cpu().numpy(), g[k]), k
+    conics, radii = gsplat.compute_cov2d_bounds(cu(golden("cov2d_bounds.npz")["cov2d"]))
+    gg = golden("cov2d_bounds.npz")
+    close(conics.cpu().numpy()[gg["valid"]], gg["conics"][gg["valid"]], 5e-4, 1e-5, "conics")
+    close(radii.cpu().numpy()[gg["valid"], 0], gg["radii"][gg["valid"]], 5e-4, 0, "radii")
+
+
+BLEND_CASES = [
+    ("c1", None, False, None, None, None),          # BASELINE config 1: 10k, 256^2, S=1, static
+    ("c2", 40000, True, 5, 0.0, 1 / 60),            # blur only
+    ("c2", 40000, True, 1, 1 / 50, 0.0),            # rolling shutter only
+    ("c2", 40000, True, 10, 1 / 50, 1 / 60),        # both, kernel maximum S
+    ("c2", 40000, True, 3, 1 / 50, 1 / 60),
+]
+
+
+def _gpu_blend_from_oracle_inputs(d, r, S):
+    b = r["bins"]
+    tb = ((d["W"] + 15) // 16, (d["H"] + 15) // 16, 1)
+    return _C.rasterize_forward(tb, (16, 16, 1), (d["W"], d["H"], 1), S, cu(b["gaussian_ids_sorted"]), cu(b["tile_bins"]),
+                                cu(r["proj"]["xys"]), cu(r["proj"]["pix_vels"]), d["rs"], d["exposure"],
+                                cu(r["proj"]["conics"]), cu(r["colors"]), cu(r["opac"]), cu(d["background"]))
+
+
+@pytest.mark.parametrize("name,n,motion,S,rs,exposure", BLEND_CASES)
+def test_blend_forward_vs_oracle(name, n, motion, S, rs, exposure):
+    d = scene_np(name, n=n, motion=motion, S=S, rs=rs, exposure=exposure, H=256 if n else None, W=320 if n else None)
+    r = oracle_render(d)
+    img, Ts, fi = _gpu_blend_from_oracle_inputs(d, r, d["S"])
+    assert frac_mismatch(fi.cpu().numpy(), r["final_idx"]) <= 2e-4, "final_idx"
+    same = fi.cpu().numpy() == r["final_idx"]
+    close(Ts.cpu().numpy()[same], r["final_Ts"][same], 1e-6, 2e-5, "final_Ts")
+    px_same = same.all(-1)
+    close(img.cpu().numpy()[px_same], r["img"][px_same], 2e-5, 1e-5, "out_img")
+    mse = float(((img.cpu().numpy().astype(np.float64) - r["img"]) ** 2).mean())
+    assert mse < 1e-9, f"PSNR {10 * np.log10(1.0 / max(mse, 1e-30)):.1f} dB"
+
+
+@pytest.mark.parametrize("name,n,motion,S,rs,exposure", BLEND_CASES)
+def test_blend_backward_vs_oracle(name, n, motion, S, rs, exposure):
+    d = scene_np(name, n=n, motion=motion, S=S, rs=rs, exposure=exposure, H=256 if n else None, W=320 if n else None)
+    r = oracle_render(d)
+    g = np.random.default_rng(11)
+    v_out = g.standard_normal((d["H"], d["W"], 3)).astype(np.float32)
+    v_alpha = g.standard_normal((d["H"], d["W"])).astype(np.float32)
+    b = r["bins"]
+    # feed the ORACLE's forward state so only the backward kernel is under test
+    ref = O.rasterize_backward(d["H"], d["W"], 16, d["S"], b["gaussian_ids_sorted"], b["tile_bins"], r["proj"]["xys"],
+                               r["proj"]["pix_vels"], d["rs"], d["exposure"], r["proj"]["conics"], r["colors"], r["opac"],
+                               d["background"], r["final_Ts"], r["final_idx"], v_out, v_alpha)
+    out = _C.rasterize_backward(d["H"], d["W"], 16, d["S"], cu(b["gaussian_ids_sorted"]), cu(b["tile_bins"]),
+                                cu(r["proj"]["xys"]), cu(r["proj"]["pix_vels"]), d["rs"], d["exposure"],
+                                cu(r["proj"]["conics"]), cu(r["colors"]), cu(r["opac"]), cu(d["background"]),
+                                cu(r["final_Ts"]), cu(r["final_idx"]), cu(v_out), cu(v_alpha))
+    for t, k in zip(out, ["v_xy", "v_xy_abs", "v_pix_vels", "v_conic", "v_colors", "v_opacity"]):
+        grad_close(t, ref[k], 1e-3, k)
+
+
+def test_end_to_end_autograd_vs_oracle_chain():
+    """project -> SH -> rasterize through the public operators, loss.backward(), vs the oracle chain."""
+    d = scene_np("c2", n=30000, H=192, W=256)
+    r = oracle_render(d)
+    means = cu(d["means"]).requires_grad_(True)
+    scales = cu(d["scales"]).requires_grad_(True)
+    quats = cu(d["quats"]).requires_grad_(True)
+    sh = cu(d["sh"]).requires_grad_(True)
+    opac = cu(d["opacity"]).requires_grad_(True)
+    bg = cu(d["background"]).requires_grad_(True)
+    xys, depths, pix_vels, radii, conics, comp, nth, cov3d = gpu_project(d, means=means, scales=scales, quats=quats)
+    xys.retain_grad()
+    rgbs = torch.clamp(spherical_harmonics(3, means.detach() - cu(d["cam_pos"]), sh) + 0.5, min=0.0)
+    img, alpha = rasterize_gaussians(xys, depths, pix_vels, radii, conics, nth, rgbs, opac * comp[:, None], d["H"], d["W"],
+                                     16, background=bg, return_alpha=True, rolling_shutter_time=d["rs"],
+                                     exposure_time=d["exposure"], blur_samples=d["S"])
+    close(img, r["img"], 5e-5, 1e-4, "e2e image")
+    close(alpha, 1 - r["final_Ts"].mean(-1), 5e-5, 1e-4, "e2e alpha")
+    g = np.random.default_rng(5)
+    v_out = g.standard_normal(r["img"].shape).astype(np.float32)
+    v_alpha = g.standard_normal(r["img"].shape[:2]).astype(np.float32)
+    ((img * cu(v_out)).sum() + (alpha * cu(v_alpha)).sum()).backward()
+    b = r["bins"]
+    # d(alpha)/d(final_Ts) = -1/S is folded into the kernel through v_out_alpha exactly like the reference
+    rb = O.rasterize_backward(d["H"], d["W"], 16, d["S"], b["gaussian_ids_sorted"], b["tile_bins"], r["proj"]["xys"],
+                              r["proj"]["pix_vels"], d["rs"], d["exposure"], r["proj"]["conics"], r["colors"], r["opac"],
+                              d["background"], r["final_Ts"], r["final_idx"], v_out, v_alpha)
+    grad_close(xys.grad, rb["v_xy"], 2e-3, "v_xy through autograd")
+    grad_close(xys.absgrad, rb["v_xy_abs"], 2e-3, "xys.absgrad side channel")
+    # SH coefficient gradient: clamp(rgb + 0.5, 0) gate, then basis outer product
+    gate = (r["colors"] > 0).astype(np.float32)
+    ref_sh = O.sh_backward("fast", 3, 3, d["means"] - d["cam_pos"][None], rb["v_colors"] * gate)
+    grad_close(sh.grad, ref_sh, 2e-3, "v_sh")
+    grad_close(opac.grad, rb["v_opacity"][:, 0:1] * r["proj"]["compensation"][:, None], 2e-3, "v_opacity logit side")
+    ref_bg = (v_out.reshape(-1, 3).astype(np.float64) * r["final_Ts"].mean(-1).reshape(-1, 1)).sum(0)
+    grad_close(bg.grad, ref_bg, 2e-3, "v_background")
+    pb = O.project_backward(d["means"], d["scales"], 1.0, d["quats"], d["lin_vel"], d["ang_vel"], d["rs"], d["exposure"],
+                            d["viewmat"], d["fx"], d["fy"], r["proj"]["cov3d"], r["proj"]["radii"], r["proj"]["conics"],
+                            r["proj"]["compensation"], rb["v_xy"], np.zeros(d["N"], np.float32), rb["v_pix_vels"],
+                            rb["v_conic"], (rb["v_opacity"][:, 0] * d["opacity"][:, 0]).astype(np.float32))
+    grad_close(means.grad, pb["v_mean3d"], 5e-3, "v_means e2e")
+    grad_close(scales.grad, pb["v_scale"], 5e-3, "v_scales e2e")
+    grad_close(quats.grad, pb["v_quat"], 5e-3, "v_quats e2e")
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2 at full size (300k Gaussians, 800x800, S=5): size-independent properties."""
+    d = scene_np("c2")
+    out = gpu_project(d)
+    xys, depths, pix_vels, radii, conics, comp, nth, cov3d = out
+    col = cu(oracle_colors(d))
+    opac = cu(d["opacity"]) * comp[:, None]
+    bg = cu(d["background"])
+    kw = dict(background=bg, return_alpha=True, rolling_shutter_time=d["rs"], exposure_time=d["exposure"], blur_samples=d["S"])
+    img, alpha = rasterize_gaussians(xys, depths, pix_vels, radii, conics, nth, col, opac, d["H"], d["W"], 16, **kw)
+    assert torch.isfinite(img).all() and (alpha >= -1e-6).all() and (alpha <= 1 + 1e-6).all()
+    # determinism (stable sort, no atomics in the forward)
+    img2, alpha2 = rasterize_gaussians(xys, depths, pix_vels, radii, conics, nth, col, opac, d["H"], d["W"], 16, **kw)
+    assert torch.equal(img, img2) and torch.equal(alpha, alpha2)
+    # linearity in (colours, background); alpha independent of colour
+    kw2 = dict(kw, background=2 * bg)
+    img3, alpha3 = rasterize_gaussians(xys, depths, pix_vels, radii, conics, nth, 2 * col, opac, d["H"], d["W"], 16, **kw2)
+    assert torch.equal(alpha, alpha3)
+    torch.testing.assert_close(img3, 2 * img, rtol=1e-5, atol=1e-6)
+    # sortedness: within each tile the staged depths are non-decreasing
+    m, cum = gsplat.compute_cumulative_intersects(nth)
+    tb = (50, 50, 1)
+    isect, gids, isect_s, gids_s, bins = gsplat.bin_and_sort_gaussians(d["N"], m, xys, depths, radii, cum, tb, 16)
+    assert (isect_s[1:] >= isect_s[:-1]).all()
+    assert int((bins[:, 1] - bins[:, 0]).sum()) == m
+    # zero velocity: S samples collapse onto the single-sample render
+    z = torch.zeros_like(pix_vels)
+    a1 = rasterize_gaussians(xys, depths, z, radii, conics, nth, col, opac, d["H"], d["W"], 16, background=bg)
+    a5 = rasterize_gaussians(xys, depths, z, radii, conics, nth, col, opac, d["H"], d["W"], 16, background=bg,
+                             exposure_time=d["exposure"], blur_samples=5)
+    torch.testing.assert_close(a5, a1, rtol=1e-5, atol=2e-6)
+
+
+def test_empty_and_error_paths():
+    d = scene_np("c1", n=64)
+    # everything behind the camera -> no intersections -> reference's empty-render branch (rasterize.py:136-144)
+    vm = d["viewmat"].copy()
+    vm[2, 3] = -1e4
+    out = project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]), None, None, 0, 0, cu(vm), d["fx"], d["fy"],
+                            d["cx"], d["cy"], d["H"], d["W"], 16)
+    xys, depths, pix_vels, radii, conics, comp, nth, cov3d = out
+    assert int(nth.sum()) == 0 and int(radii.sum()) == 0
+    bg = cu(d["background"])
+    img, alpha = rasterize_gaussians(xys, depths, pix_vels, radii, conics, nth, cu(oracle_colors(d)), cu(d["opacity"]),
+                                     d["H"], d["W"], 16, background=bg, return_alpha=True)
+    assert torch.allclose(img, bg.expand_as(img)) and (alpha == 1).all()
+    with pytest.raises(AssertionError):
+        project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]), None, None, 0, 0, cu(vm), 1, 1, 0, 0, 8, 8, 17)
+    with pytest.raises(AssertionError):
+        project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]) * 2, None, None, 0, 0, cu(vm), 1, 1, 0, 0, 8, 8, 16)
+    with pytest.raises(RuntimeError, match="unsupported blur size"):
+        rasterize_gaussians(xys, depths, pix_vels, radii + 1, conics, nth + 1, cu(oracle_colors(d)), cu(d["opacity"]),
+                            d["H"], d["W"], 16, exposure_time=0.1, blur_samples=11)
+    with pytest.raises(ValueError):
+        rasterize_gaussians(xys[:, :1], depths, pix_vels, radii, conics, nth, cu(oracle_colors(d)), cu(d["opacity"]), 8, 8, 16)
+
+
+@pytest.mark.parametrize("bw,H,W", [(16, 100, 75), (8, 40, 56), (5, 33, 17), (2, 9, 7)])
+def test_ragged_sizes_and_small_tiles(bw, H, W):
+    """Image sizes that are not tile multiples and every supported block_width family."""
+    d = scene_np("c1", n=3000, H=H, W=W)
+    d["bw"] = bw
+    r = oracle_render(d)
+    b = r["bins"]
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    img, Ts, fi = _C.rasterize_forward(tb, (bw, bw, 1), (W, H, 1), 1, cu(b["gaussian_ids_sorted"]), cu(b["tile_bins"]),
+                                       cu(r["proj"]["xys"]), cu(r["proj"]["pix_vels"]), 0.0, 0.0, cu(r["proj"]["conics"]),
+                                       cu(r["colors"]), cu(r["opac"]), cu(d["background"]))
+    assert frac_mismatch(fi.cpu().numpy(), r["final_idx"]) <= 1e-3
+    close(img, r["img"], 5e-5, 1e-4, "ragged image")
+
+
+def test_nd_rasterize_vs_oracle():
+    d = scene_np("c1", n=4000, H=64, W=80)
+    r = oracle_render(d)
+    g = np.random.default_rng(2)
+    C = 5
+    cols = g.uniform(0, 1, (d["N"], C)).astype(np.float32)
+    bgc = g.uniform(0, 1, C).astype(np.float32)
+    b = r["bins"]
+    ref = O.nd_rasterize_forward(d["H"], d["W"], 16, b["gaussian_ids_sorted"], b["tile_bins"], r["proj"]["xys"],
+                                 r["proj"]["conics"], cols, r["opac"], bgc)
+    tb = ((d["W"] + 15) // 16, (d["H"] + 15) // 16, 1)
+    out = _C.nd_rasterize_forward(tb, (16, 16, 1), (d["W"], d["H"], 1), 1, cu(b["gaussian_ids_sorted"]), cu(b["tile_bins"]),
+                                  cu(r["proj"]["xys"]), cu(r["proj"]["pix_vels"]), 0.0, 0.0, cu(r["proj"]["conics"]),
+                                  cu(cols), cu(r["opac"]), cu(bgc))
+    assert frac_mismatch(out[2].cpu().numpy(), ref[2]) <= 1e-3
+    close(out[0], ref[0], 2e-2, 1e-2, "nd image (fp16 accumulators)")
+    v_out = g.standard_normal((d["H"], d["W"], C)).astype(np.float32)
+    v_alpha = g.standard_normal((d["H"], d["W"])).astype(np.float32)
+    rb = O.nd_rasterize_backward(d["H"], d["W"], 16, b["gaussian_ids_sorted"], b["tile_bins"], r["proj"]["xys"],
+                                 r["proj"]["conics"], cols, r["opac"], bgc, ref[1], ref[2], v_out, v_alpha)
+    ob = _C.nd_rasterize_backward(d["H"], d["W"], 16, 1, cu(b["gaussian_ids_sorted"]), cu(b["tile_bins"]),
+                                  cu(r["proj"]["xys"]), cu(r["proj"]["pix_vels"]), 0.0, 0.0, cu(r["proj"]["conics"]),
+                                  cu(cols), cu(r["opac"]), cu(bgc), cu(ref[1]), cu(ref[2]), cu(v_out), cu(v_alpha))
+    for t, k in zip([ob[0], ob[1], ob[3], ob[4], ob[5]], ["v_xy", "v_xy_abs", "v_conic", "v_colors", "v_opacity"]):
+        grad_close(t, rb[k], 2e-2, "nd " + k)
+    with pytest.raises(RuntimeError, match="blur not supported"):
+        _C.nd_rasterize_forward(tb, (16, 16, 1), (d["W"], d["H"], 1), 2, cu(b["gaussian_ids_sorted"]), cu(b["tile_bins"]),
+                                cu(r["proj"]["xys"]), cu(r["proj"]["pix_vels"]), 0.0, 0.1, cu(r["proj"]["conics"]),
+                                cu(cols), cu(r["opac"]), cu(bgc))
