@@ -1,6 +1,8 @@
 // ABI version + thread-local error string of libb200splat.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -13,5 +15,10 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace b200
 
+namespace b200 {
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace b200
+extern "C" long long b200_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
 extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
 extern "C" const char *b200_last_error(void) { return b200::g_err; }

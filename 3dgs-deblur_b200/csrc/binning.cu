@@ -86,6 +86,7 @@ extern "C" int b200_cumulative_intersects(int num_points, const int32_t *num_til
     B200_REQUIRE(num_tiles_hit && cum_tiles_hit && temp, "null pointer");
     cudaStream_t st = as_stream(stream);
     B200_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, num_tiles_hit, cum_tiles_hit, num_points, st));
+    count_launch(2);  // decoupled look-back scan: init + scan kernels
     if (total_host_pinned)
         B200_CUDA(cudaMemcpyAsync(total_host_pinned, cum_tiles_hit + (num_points - 1), sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, st));
@@ -128,6 +129,7 @@ extern "C" int b200_sort_intersects(int num_intersects, int num_tiles, const int
                                               reinterpret_cast<uint64_t *>(isect_ids_sorted), gaussian_ids,
                                               gaussian_ids_sorted, num_intersects, 0, key_end_bit(num_tiles),
                                               as_stream(stream)));
+    count_launch(1 + (key_end_bit(num_tiles) + 7) / 8);  // onesweep: histogram + one pass per 8-bit digit
     return B200_OK;
 }
 

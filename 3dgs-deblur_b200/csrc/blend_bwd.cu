@@ -110,16 +110,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
     const int wmax = __reduce_max_sync(0xffffffffu, my_max);  // last contributor over the warp's pixel-samples
     if (lane == 0) s_max[warp] = wmax;
 
-    WarpWindow win;
-    {
-        const float big = 3.0e38f;
-        win.x0 = warp_min(inside ? px : big); win.x1 = warp_max(inside ? px : -big);
-        win.y0 = warp_min(inside ? py : big); win.y1 = warp_max(inside ? py : -big);
-        float tlo = big, thi = -big;
-#pragma unroll
-        for (int s = 0; s < S; ++s) { tlo = fminf(tlo, tau[s]); thi = fmaxf(thi, tau[s]); }
-        win.t0 = warp_min(inside ? tlo : big); win.t1 = warp_max(inside ? thi : -big);
-    }
+    const WarpWindow win = warp_window(inside, px, py, roll);
 
     if (tid == 0) {
 #pragma unroll
@@ -171,11 +162,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
         if (wmax >= range.x) {
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int e = c0 + lane;
-                const bool keep = (e < cnt) && (top - e <= wmax) && may_touch(s_rec[st][e], win);
-                unsigned m = __ballot_sync(0xffffffffu, keep);
+                const unsigned my_mask =
+                    ((e < cnt) && (top - e <= wmax)) ? sample_mask<S>(s_rec[st][e], win, p.g.exposure) : 0u;
+                unsigned m = __ballot_sync(0xffffffffu, my_mask != 0u);
                 while (m) {
-                    const int k = c0 + (__ffs(m) - 1);
+                    const int src = __ffs(m) - 1;
+                    const int k = c0 + src;
                     m &= m - 1;
+                    const unsigned smask = __shfl_sync(0xffffffffu, my_mask, src);
                     const int idx = top - k;
                     const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
@@ -187,7 +181,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
                     bool any = false;
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        if (idx > bin_final[s]) continue;  // backward.cu:252-254 (bin_final = -1 outside the image)
+                        if (!(smask & (1u << s)) || idx > bin_final[s]) continue;  // backward.cu:252-254 (bin_final = -1 outside)
                         const float dx = A.x + tau[s] * A.z - px;
                         const float dy = A.y + tau[s] * A.w - py;
                         const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;

@@ -62,6 +62,7 @@ static inline int launch_pack(int n, const float *xys, const float *pix_vels, co
     pack_records_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, reinterpret_cast<const float2 *>(xys),
                                                           reinterpret_cast<const float2 *>(pix_vels), conics, colors,
                                                           opac, reinterpret_cast<PackedGaussian *>(packed_ws));
+    count_launch(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("pack_records_kernel launch failed: %s", cudaGetErrorString(e));
@@ -98,20 +99,45 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// Rectangle (pixel centres) and time window covered by the live lanes of this warp.
+// Rectangle (pixel centres) covered by the live lanes of this warp and the range of their rolling-shutter
+// time offsets (forward.cu:360 `roll_time`; constant within an image row).
 struct WarpWindow {
-    float x0, x1, y0, y1, t0, t1;
+    float x0, x1, y0, y1, r0, r1;
 };
 
-// Conservative test: can Gaussian `g` reach alpha >= 1/255 for any pixel centre / sample time in `w`?
-// Written so that NaNs compare "keep".
-__device__ __forceinline__ bool may_touch(const PackedGaussian &g, const WarpWindow &w) {
-    const float ax = w.t0 * g.vx, bx = w.t1 * g.vx, ay = w.t0 * g.vy, by = w.t1 * g.vy;
-    const float cx0 = g.x + fminf(ax, bx), cx1 = g.x + fmaxf(ax, bx);
-    const float cy0 = g.y + fminf(ay, by), cy1 = g.y + fmaxf(ay, by);
-    const bool out = (g.hx < 0.f) || (cx0 - g.hx > w.x1) || (cx1 + g.hx < w.x0) || (cy0 - g.hy > w.y1) ||
-                     (cy1 + g.hy < w.y0);
-    return !out;
+__device__ __forceinline__ WarpWindow warp_window(bool live, float px, float py, float roll) {
+    const float big = 3.0e38f;
+    WarpWindow w;
+    w.x0 = warp_min(live ? px : big); w.x1 = warp_max(live ? px : -big);
+    w.y0 = warp_min(live ? py : big); w.y1 = warp_max(live ? py : -big);
+    w.r0 = warp_min(live ? roll : big); w.r1 = warp_max(live ? roll : -big);
+    return w;
+}
+
+// blur_rel of forward.cu:363 without the rolling-shutter part
+template <int S>
+__device__ __forceinline__ float blur_offset(int s, float exposure) {
+    return (S > 1) ? ((float)s / (float)(S - 1) - 0.5f) * exposure : 0.0f;
+}
+
+// Conservative per-sample cull: bit s is set unless Gaussian `g` provably cannot reach alpha >= 1/255 at any pixel
+// centre of the window for blur sample s (its centre moves along g.v over the window's rolling-shutter times).
+// Float adds are monotonic, so [blur_s + r0, blur_s + r1] bounds every lane's tau[s] exactly.  NaNs compare "keep".
+template <int S>
+__device__ __forceinline__ unsigned sample_mask(const PackedGaussian &g, const WarpWindow &w, float exposure) {
+    if (g.hx < 0.f) return 0u;
+    unsigned m = 0u;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const float b = blur_offset<S>(s, exposure);
+        const float t0 = b + w.r0, t1 = b + w.r1;
+        const float ax = t0 * g.vx, bx = t1 * g.vx, ay = t0 * g.vy, by = t1 * g.vy;
+        const float cx0 = g.x + fminf(ax, bx), cx1 = g.x + fmaxf(ax, bx);
+        const float cy0 = g.y + fminf(ay, by), cy1 = g.y + fmaxf(ay, by);
+        const bool out = (cx0 - g.hx > w.x1) || (cx1 + g.hx < w.x0) || (cy0 - g.hy > w.y1) || (cy1 + g.hy < w.y0);
+        m |= out ? 0u : (1u << s);
+    }
+    return m;
 }
 
 #endif

@@ -48,17 +48,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const Blen
     for (int s = 0; s < S; ++s)
         tau[s] = ((S > 1) ? ((float)s / (float)(S - 1) - 0.5f) * p.g.exposure : 0.0f) + roll;
 
-    // the warp's pixel rectangle and time window (live lanes only)
-    WarpWindow win;
-    {
-        const float big = 3.0e38f;
-        win.x0 = warp_min(inside ? px : big); win.x1 = warp_max(inside ? px : -big);
-        win.y0 = warp_min(inside ? py : big); win.y1 = warp_max(inside ? py : -big);
-        float tlo = big, thi = -big;
-#pragma unroll
-        for (int s = 0; s < S; ++s) { tlo = fminf(tlo, tau[s]); thi = fmaxf(thi, tau[s]); }
-        win.t0 = warp_min(inside ? tlo : big); win.t1 = warp_max(inside ? thi : -big);
-    }
+    // the warp's pixel rectangle and rolling-shutter window (live lanes only)
+    const WarpWindow win = warp_window(inside, px, py, roll);
 
     const int2 range = p.tile_bins[tile];
     const int total = range.y - range.x;
@@ -104,18 +95,20 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const Blen
         if (__any_sync(0xffffffffu, alive != 0u)) {
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int e = c0 + lane;
-                const bool keep = (e < cnt) && may_touch(s_rec[st][e], win);
-                unsigned m = __ballot_sync(0xffffffffu, keep);
+                const unsigned my_mask = (e < cnt) ? sample_mask<S>(s_rec[st][e], win, p.g.exposure) : 0u;
+                unsigned m = __ballot_sync(0xffffffffu, my_mask != 0u);
                 while (m) {
-                    const int k = c0 + (__ffs(m) - 1);
+                    const int src = __ffs(m) - 1;
+                    const int k = c0 + src;
                     m &= m - 1;
+                    const unsigned live = alive & __shfl_sync(0xffffffffu, my_mask, src);
                     const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
                     const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
                     const float cut = C.w + 1e-4f;
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        if (!(alive & (1u << s))) continue;
+                        if (!(live & (1u << s))) continue;
                         const float dx = A.x + tau[s] * A.z - px;
                         const float dy = A.y + tau[s] * A.w - py;
                         const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;

@@ -10,6 +10,7 @@ namespace b200 {
 
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char *fmt, ...);
+void count_launch(int n);
 
 #define B200_REQUIRE(cond, ...)              \
     do {                                     \
@@ -28,7 +29,11 @@ void set_error(const char *fmt, ...);
         }                                                                                   \
     } while (0)
 
-#define B200_LAUNCH_CHECK() B200_CUDA(cudaGetLastError())
+#define B200_LAUNCH_CHECK()          \
+    do {                             \
+        b200::count_launch(1);       \
+        B200_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

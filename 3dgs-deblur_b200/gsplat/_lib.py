@@ -17,6 +17,7 @@ _p, _i, _u, _f, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_size_t
 SIGNATURES = {
     "b200_abi_version": (_i, []),
     "b200_last_error": (C.c_char_p, []),
+    "b200_launch_count": (C.c_longlong, []),
     "b200_packed_record_bytes": (_sz, []),
     "b200_project_gaussians_forward": (_i, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _p, _f, _f, _f, _f, _u, _u, _u, _f,
                                             _p, _p, _p, _p, _p, _p, _p, _p, _p]),

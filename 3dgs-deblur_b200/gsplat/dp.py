@@ -1,0 +1,135 @@
+"""Image-sharded data-parallel training dispatcher for the rasterizer hot path.
+
+Replaces the reference's one-random-image-per-step dispatcher (nerfstudio/data/datamanagers/
+full_images_datamanager.py:287-304) + the DDP wrap Splatfacto cannot actually use
+(pipelines/base_pipeline.py:282-284; SURVEY section 5 "distributed") for this path:
+
+  * all Gaussian parameters (means 3, log-scales 3, quats 4, SH dc 3, SH rest 3(K-1), opacity 1 = 59
+    floats per Gaussian at K=16) live in ONE flat fp32 buffer, their gradients in a second one;
+  * every rank renders its own image of the step (rank r takes image step*R + r) through the public
+    gsplat operators -- the render block of splatfacto.py:816-880 -- and back-propagates;
+  * ONE allreduce(sum) over the flat gradient buffer per step (NCCL over NVLink on GPUs, gloo in the CPU
+    tests), then the same fused Adam step on every rank, so replicas stay bit-identical;
+  * per-camera parameters (velocities) are disjoint rows: their gradients ride in the same buffer.
+
+The densification statistics (xys.absgrad norms, visibility counts, max 2D radius;
+splatfacto.py:417-434) are exposed by `reduce_densify_stats` with the matching sum / sum / max
+reductions so a caller can keep topology changes identical across ranks.
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+FIELDS = (("means", 3), ("log_scales", 3), ("quats", 4), ("sh_dc", 3), ("sh_rest", None), ("opacity_logit", 1))
+
+
+class FlatGaussians:
+    """Gaussian parameters as views into one flat buffer (+ a flat gradient buffer of the same layout)."""
+
+    def __init__(self, scene: Dict, device, n_cameras: int = 0, optimize_velocities: bool = False):
+        N = scene["means"].shape[0]
+        K = scene["sh_rest"].shape[1] + 1
+        self.N, self.K = N, K
+        widths = [3, 3, 4, 3, 3 * (K - 1), 1]
+        extra = 6 * n_cameras if optimize_velocities else 0
+        total = N * sum(widths) + extra
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.params: Dict[str, torch.Tensor] = {}
+        off = 0
+        src = dict(means=scene["means"], log_scales=scene["log_scales"], quats=scene["quats"], sh_dc=scene["sh_dc"],
+                   sh_rest=scene["sh_rest"], opacity_logit=scene["opacity_logit"])
+        shapes = dict(means=(N, 3), log_scales=(N, 3), quats=(N, 4), sh_dc=(N, 1, 3), sh_rest=(N, K - 1, 3),
+                      opacity_logit=(N, 1))
+        for (name, _), w in zip(FIELDS, widths):
+            view = self.flat[off:off + N * w].view(shapes[name])
+            view.copy_(src[name].to(device).reshape(shapes[name]))
+            p = view.requires_grad_(True)
+            p.grad = self.flat_grad[off:off + N * w].view(shapes[name])
+            self.params[name] = p
+            off += N * w
+        self.cam_vel: Optional[torch.Tensor] = None
+        if extra:
+            view = self.flat[off:off + extra].view(n_cameras, 6)
+            p = view.requires_grad_(True)
+            p.grad = self.flat_grad[off:off + extra].view(n_cameras, 6)
+            self.cam_vel = p
+        self.floats_per_gaussian = sum(widths)
+
+    def parameters(self) -> List[torch.Tensor]:
+        ps = list(self.params.values())
+        if self.cam_vel is not None:
+            ps.append(self.cam_vel)
+        return ps
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+
+def render(model: FlatGaussians, cam: Dict, scene: Dict, cam_index: int = 0, sh_degree_to_use: int = 3):
+    """The Splatfacto render block (splatfacto.py:816-880) on the public operators.  Returns (rgb, alpha, xys)."""
+    from gsplat import project_gaussians, rasterize_gaussians, spherical_harmonics
+
+    p = model.params
+    if model.cam_vel is not None:
+        vel = model.cam_vel[cam_index] + cam["vel0"]
+        lin, ang = vel[:3].unsqueeze(0), vel[3:].unsqueeze(0)
+    else:
+        lin, ang = cam["lin_vel"].unsqueeze(0), cam["ang_vel"].unsqueeze(0)
+    H, W, bw = scene["H"], scene["W"], scene["block_width"]
+    quats = p["quats"] / p["quats"].norm(dim=-1, keepdim=True)
+    xys, depths, pix_vels, radii, conics, comp, num_tiles_hit, _ = project_gaussians(
+        p["means"], torch.exp(p["log_scales"]), 1, quats, lin, ang, scene["rolling_shutter_time"],
+        scene["exposure_time"], cam["viewmat"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, bw)
+    colors = torch.cat((p["sh_dc"], p["sh_rest"]), dim=1)
+    viewdirs = p["means"].detach() - cam["cam_pos"]
+    rgbs = torch.clamp(spherical_harmonics(sh_degree_to_use, viewdirs, colors) + 0.5, min=0.0)
+    opacities = torch.sigmoid(p["opacity_logit"]) * comp[:, None]  # "antialiased" mode, splatfacto.py:853-854
+    blur = scene["blur_samples"] if scene["exposure_time"] > 0 else 1
+    rgb, alpha = rasterize_gaussians(xys, depths, pix_vels, radii, conics, num_tiles_hit, rgbs, opacities, H, W, bw,
+                                     rolling_shutter_time=scene["rolling_shutter_time"],
+                                     exposure_time=scene["exposure_time"], blur_samples=blur,
+                                     background=scene["background"], return_alpha=True)
+    return rgb, alpha, xys, radii
+
+
+class ImageShardedTrainer:
+    """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient allreduce per step."""
+
+    def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, comm_stream: bool = True):
+        self.model, self.scene = model, scene
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = group
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        fused = model.flat.is_cuda
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-15, fused=fused)
+        self.step_idx = 0
+
+    def image_index(self, step: int, n_images: int) -> int:
+        return (step * self.world + self.rank) % n_images
+
+    def train_step(self, cam: Dict, target: torch.Tensor, cam_index: int = 0):
+        """fwd + L1 loss + bwd (+ allreduce) + Adam.  Returns the (device) loss tensor; no host sync."""
+        m = self.model
+        m.zero_grad()
+        rgb, alpha, xys, radii = render(m, cam, self.scene, cam_index)
+        loss = (rgb - target).abs().mean()
+        loss.backward()
+        if self.distributed:
+            # gradients of the R images are averaged (each rank's loss is a per-image mean)
+            dist.all_reduce(m.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            m.flat_grad.mul_(1.0 / self.world)
+        self.opt.step()
+        self.step_idx += 1
+        self.last_xys, self.last_radii = xys, radii
+        return loss
+
+    def reduce_densify_stats(self, grad_norm_sum: torch.Tensor, vis_counts: torch.Tensor, max_2d: torch.Tensor):
+        """sum / sum / max reductions of the densification statistics (splatfacto.py:417-434)."""
+        if self.distributed:
+            dist.all_reduce(grad_norm_sum, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(vis_counts, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(max_2d, op=dist.ReduceOp.MAX, group=self.group)
+        return grad_norm_sum, vis_counts, max_2d

@@ -50,6 +50,9 @@ extern "C" {
 
 B200_API int b200_abi_version(void);
 B200_API const char *b200_last_error(void);
+/* Number of kernels this library has launched in this process (hand-written kernels 1 each, a cub
+ * primitive counts its documented passes); bench.py reports the per-step delta as gpu_launches. */
+B200_API long long b200_launch_count(void);
 
 /* Size of one packed per-Gaussian blend record (bytes); scratch for the blend = N * this. */
 B200_API size_t b200_packed_record_bytes(void);

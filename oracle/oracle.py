@@ -163,21 +163,23 @@ def bin_and_sort(xys, depths, radii, num_tiles_hit, H, W, bw):
 
 
 def rasterize_forward(H, W, bw, S, ids_sorted, tile_bins, xys, pix_vels, rs_time, exposure, conics, colors,
-                      opacities, background):
+                      opacities, background, rows=None):
     ids_sorted, tile_bins = _i(ids_sorted), _i(tile_bins)
     xys, pix_vels, conics, colors = _f(xys), _f(pix_vels), _f(conics), _f(colors)
     opac, bg = _f(opacities).reshape(-1), _f(background)
     out_img = np.zeros((H, W, 3), np.float32)
     final_Ts = np.zeros((H, W, S), np.float32)
     final_idx = np.zeros((H, W, S), np.int32)
-    lib().orc_rasterize_forward(C.c_int(H), C.c_int(W), C.c_int(bw), C.c_int(S), _p(ids_sorted), _p(tile_bins),
-                                _p(xys), _p(pix_vels), C.c_float(rs_time), C.c_float(exposure), _p(conics),
-                                _p(colors), _p(opac), _p(bg), _p(out_img), _p(final_Ts), _p(final_idx))
+    r0, r1 = (0, H) if rows is None else rows
+    lib().orc_rasterize_forward_rows(C.c_int(r0), C.c_int(r1), C.c_int(H), C.c_int(W), C.c_int(bw), C.c_int(S),
+                                     _p(ids_sorted), _p(tile_bins), _p(xys), _p(pix_vels), C.c_float(rs_time),
+                                     C.c_float(exposure), _p(conics), _p(colors), _p(opac), _p(bg), _p(out_img),
+                                     _p(final_Ts), _p(final_idx))
     return out_img, final_Ts, final_idx
 
 
 def rasterize_backward(H, W, bw, S, ids_sorted, tile_bins, xys, pix_vels, rs_time, exposure, conics, colors,
-                       opacities, background, final_Ts, final_idx, v_out, v_out_alpha):
+                       opacities, background, final_Ts, final_idx, v_out, v_out_alpha, rows=None):
     ids_sorted, tile_bins = _i(ids_sorted), _i(tile_bins)
     xys, pix_vels, conics, colors = _f(xys), _f(pix_vels), _f(conics), _f(colors)
     opac, bg = _f(opacities).reshape(-1), _f(background)
@@ -186,8 +188,9 @@ def rasterize_backward(H, W, bw, S, ids_sorted, tile_bins, xys, pix_vels, rs_tim
     out = dict(v_xy=np.zeros((n, 2), np.float32), v_xy_abs=np.zeros((n, 2), np.float32),
                v_pix_vels=np.zeros((n, 2), np.float32), v_conic=np.zeros((n, 3), np.float32),
                v_colors=np.zeros((n, 3), np.float32), v_opacity=np.zeros((n, 1), np.float32))
-    lib().orc_rasterize_backward(
-        C.c_int(n), C.c_int(H), C.c_int(W), C.c_int(bw), C.c_int(S), _p(ids_sorted), _p(tile_bins), _p(xys),
+    r0, r1 = (0, H) if rows is None else rows
+    lib().orc_rasterize_backward_rows(
+        C.c_int(r0), C.c_int(r1), C.c_int(n), C.c_int(H), C.c_int(W), C.c_int(bw), C.c_int(S), _p(ids_sorted), _p(tile_bins), _p(xys),
         _p(pix_vels), C.c_float(rs_time), C.c_float(exposure), _p(conics), _p(colors), _p(opac), _p(bg),
         _p(final_Ts), _p(final_idx), _p(v_out), _p(v_out_alpha), _p(out["v_xy"]), _p(out["v_xy_abs"]),
         _p(out["v_pix_vels"]), _p(out["v_conic"]), _p(out["v_colors"]), _p(out["v_opacity"]))

@@ -1,0 +1,64 @@
+"""`bench.py --impl refgpu`: the train step of bench.py on the UNMODIFIED reference CUDA kernels (oracle/_ref),
+same scene, same loss, same fused Adam, 1 GPU.  BENCH INFRASTRUCTURE ONLY (see ref_ops.py)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(args):
+    sys.path.insert(0, os.path.join(ROOT, "3dgs-deblur_b200"))
+    import ref_ops
+    from gsplat import synthetic
+    from gsplat.dp import FlatGaussians
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n_img = args.images
+    scene = synthetic.make_scene(args.config, device="cpu", n_override=args.n, n_cameras=n_img)
+    scene_dev = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in scene.items() if k != "cameras"}
+    cams = [dict(viewmat=c["viewmat"].to(dev), fx=c["fx"], fy=c["fy"], cx=c["cx"], cy=c["cy"], cam_pos=c["cam_pos"].to(dev),
+                 lin_vel=c["lin_vel"].to(dev), ang_vel=c["ang_vel"].to(dev)) for c in scene["cameras"]]
+    targets = [c["target"].to(dev) for c in scene["cameras"]]
+    model = FlatGaussians(scene_dev, dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-15, fused=True)
+
+    def step(k):
+        i = k % n_img
+        model.zero_grad()
+        rgb, alpha = ref_ops.render(model, cams[i], scene_dev)
+        loss = (rgb - targets[i]).abs().mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+
+    # per-kernel breakdown of one step with the torch profiler (names of the reference's own kernels)
+    from torch.profiler import ProfilerActivity, profile
+
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for k in range(3):
+            step(k)
+        torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
+    kernels = {r.key[:60]: round(r.device_time_total / 3 / 1000.0, 4) for r in rows}
+    out = {"impl": "refgpu", "metric": "train images/sec (fwd+bwd) at N=5 blur samples", "value": 1000.0 / ms, "unit": "images/s",
+           "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "config": {"workload": f"{args.config}: {scene['N']} Gaussians, {scene['W']}x{scene['H']}, S={scene['blur_samples']}",
+                      "arm": "unmodified reference gsplat CUDA kernels (oracle/_ref, -O3 --use_fast_math, sm_100), velocities constant "
+                             "(the reference's faster mode), same L1 loss + fused Adam"},
+           "kernels_ms_per_step": kernels}
+    print(json.dumps(out), flush=True)

@@ -398,20 +398,29 @@ void orc_map_intersects(int n, const float *xys, const float *depths, const int 
     }
 }
 
-typedef struct { int64_t key; int32_t val; int32_t pos; } orc_kv;
-static int kv_cmp(const void *a, const void *b) {
-    const orc_kv *x = (const orc_kv *)a, *y = (const orc_kv *)b;
-    if (x->key != y->key) return x->key < y->key ? -1 : 1;
-    return x->pos < y->pos ? -1 : (x->pos > y->pos ? 1 : 0); /* stable */
-}
-
-/* utils.py:179-180 : ascending sort by key, values gathered; ties broken by input position */
+/* utils.py:179-180 : ascending sort by key, values gathered; ties keep input order (stable LSD radix sort,
+ * 8-bit digits over the non-negative 64-bit keys) */
 void orc_sort_intersects(int m, const int64_t *keys, const int32_t *vals, int64_t *keys_out, int32_t *vals_out) {
-    orc_kv *kv = (orc_kv *)malloc(sizeof(orc_kv) * (size_t)(m > 0 ? m : 1));
-    for (int i = 0; i < m; ++i) { kv[i].key = keys[i]; kv[i].val = vals[i]; kv[i].pos = i; }
-    qsort(kv, (size_t)m, sizeof(orc_kv), kv_cmp);
-    for (int i = 0; i < m; ++i) { keys_out[i] = kv[i].key; vals_out[i] = kv[i].val; }
-    free(kv);
+    if (m <= 0) return;
+    uint64_t *ka = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)m), *kb = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)m);
+    int32_t *va = (int32_t *)malloc(sizeof(int32_t) * (size_t)m), *vb = (int32_t *)malloc(sizeof(int32_t) * (size_t)m);
+    uint64_t all = 0;
+    for (int i = 0; i < m; ++i) { ka[i] = (uint64_t)keys[i]; va[i] = vals[i]; all |= ka[i]; }
+    for (int shift = 0; shift < 64; shift += 8) {
+        if (((all >> shift) & 0xff) == 0 && (all >> shift) == 0) break;
+        size_t cnt[257];
+        memset(cnt, 0, sizeof(cnt));
+        for (int i = 0; i < m; ++i) cnt[((ka[i] >> shift) & 0xff) + 1]++;
+        for (int b = 0; b < 256; ++b) cnt[b + 1] += cnt[b];
+        for (int i = 0; i < m; ++i) {
+            size_t dst = cnt[(ka[i] >> shift) & 0xff]++;
+            kb[dst] = ka[i]; vb[dst] = va[i];
+        }
+        uint64_t *tk = ka; ka = kb; kb = tk;
+        int32_t *tv = va; va = vb; vb = tv;
+    }
+    for (int i = 0; i < m; ++i) { keys_out[i] = (int64_t)ka[i]; vals_out[i] = va[i]; }
+    free(ka); free(kb); free(va); free(vb);
 }
 
 /* forward.cu:158-180 ; tile_bins (tiles,2) zero-initialised by the caller */
@@ -429,14 +438,14 @@ void orc_tile_bin_edges(int m, const int64_t *sorted, int32_t *tile_bins) {
 /* ----------------------------------------------------------- blend forward */
 
 /* forward.cu:306-456.  out_img (H,W,3), final_Ts/final_idx (H,W,S). */
-void orc_rasterize_forward(int H, int W, int bw, int S, const int32_t *ids_sorted, const int32_t *tile_bins,
-                           const float *xys, const float *pix_vels, float rs_time, float exposure,
-                           const float *conics, const float *colors, const float *opac, const float *bg,
-                           float *out_img, float *final_Ts, int32_t *final_idx) {
+static void rasterize_forward_rows(int row0, int row1, int H, int W, int bw, int S, const int32_t *ids_sorted,
+                                   const int32_t *tile_bins, const float *xys, const float *pix_vels, float rs_time,
+                                   float exposure, const float *conics, const float *colors, const float *opac,
+                                   const float *bg, float *out_img, float *final_Ts, int32_t *final_idx) {
     int tbx = (W + bw - 1) / bw;
     float avg = 1.0f / (float)S;
-#pragma omp parallel for schedule(dynamic, 4)
-    for (int i = 0; i < H; ++i) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = row0; i < row1; ++i) {
         for (int j = 0; j < W; ++j) {
             int tile = (i / bw) * tbx + (j / bw);
             int r0 = tile_bins[2 * tile], r1 = tile_bins[2 * tile + 1];
@@ -453,6 +462,8 @@ void orc_rasterize_forward(int H, int W, int bw, int S, const int32_t *ids_sorte
                     float dy = xys[2 * g + 1] + rel * pix_vels[2 * g + 1] - py;
                     const float *cn = conics + 3 * g;
                     float sigma = 0.5f * (cn[0] * dx * dx + cn[2] * dy * dy) + cn[1] * dx * dy;
+                    if (sigma > 80.f) continue; /* exp(-80) * opac < 1/255 for any finite opac <= 1e30: same skip as below,
+                                                   without libm's slow underflow path (CPU-baseline speed only) */
                     float alpha = fminf(0.999f, opac[g] * expf(-sigma));
                     if (sigma < 0.f || alpha < 1.f / 255.f) continue;
                     float nT = T * (1.f - alpha);
@@ -471,6 +482,23 @@ void orc_rasterize_forward(int H, int W, int bw, int S, const int32_t *ids_sorte
     }
 }
 
+void orc_rasterize_forward(int H, int W, int bw, int S, const int32_t *ids_sorted, const int32_t *tile_bins,
+                           const float *xys, const float *pix_vels, float rs_time, float exposure,
+                           const float *conics, const float *colors, const float *opac, const float *bg,
+                           float *out_img, float *final_Ts, int32_t *final_idx) {
+    rasterize_forward_rows(0, H, H, W, bw, S, ids_sorted, tile_bins, xys, pix_vels, rs_time, exposure, conics, colors,
+                           opac, bg, out_img, final_Ts, final_idx);
+}
+
+/* Same, restricted to image rows [row0, row1): used by bench.py to time a bounded sample of a large image. */
+void orc_rasterize_forward_rows(int row0, int row1, int H, int W, int bw, int S, const int32_t *ids_sorted,
+                                const int32_t *tile_bins, const float *xys, const float *pix_vels, float rs_time,
+                                float exposure, const float *conics, const float *colors, const float *opac,
+                                const float *bg, float *out_img, float *final_Ts, int32_t *final_idx) {
+    rasterize_forward_rows(row0 < 0 ? 0 : row0, row1 > H ? H : row1, H, W, bw, S, ids_sorted, tile_bins, xys, pix_vels,
+                           rs_time, exposure, conics, colors, opac, bg, out_img, final_Ts, final_idx);
+}
+
 /* ---------------------------------------------------------- blend backward */
 
 static inline void atomic_addd(double *p, double v) {
@@ -480,17 +508,19 @@ static inline void atomic_addd(double *p, double v) {
 
 /* backward.cu:143-369.  Outputs (float, written from double accumulators):
  * v_xy (N,2) v_xy_abs (N,2) v_pix_vel (N,2) v_conic (N,3) v_rgb (N,3) v_opac (N) */
-void orc_rasterize_backward(int n, int H, int W, int bw, int S, const int32_t *ids_sorted, const int32_t *tile_bins,
-                            const float *xys, const float *pix_vels, float rs_time, float exposure,
-                            const float *conics, const float *rgbs, const float *opac, const float *bg,
-                            const float *final_Ts, const int32_t *final_idx, const float *v_out,
-                            const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_pix_vel,
-                            float *v_conic, float *v_rgb, float *v_opac) {
+void orc_rasterize_backward_rows(int row0, int row1, int n, int H, int W, int bw, int S, const int32_t *ids_sorted,
+                                 const int32_t *tile_bins, const float *xys, const float *pix_vels, float rs_time,
+                                 float exposure, const float *conics, const float *rgbs, const float *opac,
+                                 const float *bg, const float *final_Ts, const int32_t *final_idx, const float *v_out,
+                                 const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_pix_vel,
+                                 float *v_conic, float *v_rgb, float *v_opac) {
     int tbx = (W + bw - 1) / bw;
     float avg = 1.0f / (float)S;
     double *A = (double *)calloc((size_t)n * 13, sizeof(double));
-#pragma omp parallel for schedule(dynamic, 4)
-    for (int i = 0; i < H; ++i) {
+    if (row0 < 0) row0 = 0;
+    if (row1 > H) row1 = H;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = row0; i < row1; ++i) {
         for (int j = 0; j < W; ++j) {
             int tile = (i / bw) * tbx + (j / bw);
             int r0 = tile_bins[2 * tile], r1 = tile_bins[2 * tile + 1];
@@ -511,6 +541,7 @@ void orc_rasterize_backward(int n, int H, int W, int bw, int S, const int32_t *i
                     float dx = xys[2 * g] + rel * pix_vels[2 * g] - px;
                     float dy = xys[2 * g + 1] + rel * pix_vels[2 * g + 1] - py;
                     float sigma = 0.5f * (cn[0] * dx * dx + cn[2] * dy * dy) + cn[1] * dx * dy;
+                    if (sigma > 80.f) continue; /* same outcome as the alpha < 1/255 skip below */
                     float vis = expf(-sigma);
                     float alpha = fminf(0.99f, opac[g] * vis); /* :275 -- 0.99, not 0.999 */
                     if (sigma < 0.f || alpha < 1.f / 255.f) continue;
@@ -552,6 +583,17 @@ void orc_rasterize_backward(int n, int H, int W, int bw, int S, const int32_t *i
     free(A);
 }
 
+void orc_rasterize_backward(int n, int H, int W, int bw, int S, const int32_t *ids_sorted, const int32_t *tile_bins,
+                            const float *xys, const float *pix_vels, float rs_time, float exposure,
+                            const float *conics, const float *rgbs, const float *opac, const float *bg,
+                            const float *final_Ts, const int32_t *final_idx, const float *v_out,
+                            const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_pix_vel,
+                            float *v_conic, float *v_rgb, float *v_opac) {
+    orc_rasterize_backward_rows(0, H, n, H, W, bw, S, ids_sorted, tile_bins, xys, pix_vels, rs_time, exposure, conics,
+                                rgbs, opac, bg, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_pix_vel,
+                                v_conic, v_rgb, v_opac);
+}
+
 /* ------------------------------------------------------ N-channel blend (a9) */
 
 static inline float h2f(_Float16 h) { return (float)h; }
@@ -562,7 +604,7 @@ void orc_nd_rasterize_forward(int H, int W, int bw, int C, const int32_t *ids_so
                               const float *xys, const float *conics, const float *colors, const float *opac,
                               const float *bg, float *out_img, float *final_Ts, int32_t *final_idx) {
     int tbx = (W + bw - 1) / bw;
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < H; ++i) {
         _Float16 *acc = (_Float16 *)malloc(sizeof(_Float16) * (size_t)C);
         for (int j = 0; j < W; ++j) {
@@ -601,7 +643,7 @@ void orc_nd_rasterize_backward(int n, int H, int W, int bw, int C, const int32_t
     int tbx = (W + bw - 1) / bw;
     double *A = (double *)calloc((size_t)n * 8, sizeof(double));
     double *Argb = (double *)calloc((size_t)n * C, sizeof(double));
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < H; ++i) {
         _Float16 *Sb = (_Float16 *)malloc(sizeof(_Float16) * (size_t)C);
         for (int j = 0; j < W; ++j) {
