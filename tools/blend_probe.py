@@ -1,0 +1,66 @@
+"""Stand-alone driver for the blend kernels on a BASELINE config (ncu captures / timing experiments).
+
+    python tools/blend_probe.py [--config c2] [--reps 20] [--what fwd,bwd]
+"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3dgs-deblur_b200"))
+import torch
+
+import gsplat.cuda as _C
+from gsplat import _lib, synthetic
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--what", default="fwd,bwd")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    sc = synthetic.make_scene(a.config, device=dev, n_override=a.n)
+    cam = sc["cameras"][0]
+    N, H, W, S = sc["N"], sc["H"], sc["W"], sc["blur_samples"] if sc["exposure_time"] > 0 else 1
+    rs, ex = sc["rolling_shutter_time"], sc["exposure_time"]
+    q = sc["quats"] / sc["quats"].norm(dim=-1, keepdim=True)
+    cov3d, xys, depths, pix_vels, radii, conics, comp, nth = _C.project_gaussians_forward(
+        N, sc["means"], sc["log_scales"].exp(), 1.0, q, None, None, rs, ex, cam["viewmat"], cam["fx"], cam["fy"], cam["cx"],
+        cam["cy"], H, W, 16, 0.01, _vel_tensors=(cam["lin_vel"], cam["ang_vel"]))
+    coeffs = torch.cat((sc["sh_dc"], sc["sh_rest"]), 1).contiguous()
+    colors = torch.clamp(_C.compute_sh_forward("fast", N, 3, 3, (sc["means"] - cam["cam_pos"]).contiguous(), coeffs) + 0.5, min=0)
+    opac = (torch.sigmoid(sc["opacity_logit"]) * comp[:, None]).contiguous()
+    I, cum = _C.cumulative_intersects(nth)
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    isect, gids = _C.map_gaussian_to_intersects(N, I, xys, depths, radii, cum, tb, 16)
+    isect_s, gids_s = _C.sort_intersects(tb[0] * tb[1], isect, gids)
+    bins = _C.get_tile_bin_edges(I, isect_s, tb)
+    bg = sc["background"]
+    fwd = lambda: _C.rasterize_forward(tb, (16, 16, 1), (W, H, 1), S, gids_s, bins, xys, pix_vels, rs, ex, conics, colors, opac, bg)
+    img, Ts, fi = fwd()
+    v_out = torch.sign(img - cam["target"]) / img.numel()
+    v_alpha = torch.zeros(H, W, device=dev)
+    bwd = lambda: _C.rasterize_backward(H, W, 16, S, gids_s, bins, xys, pix_vels, rs, ex, conics, colors, opac, bg, Ts, fi, v_out, v_alpha)
+    ln = (bins[:, 1] - bins[:, 0]).float()
+    print(f"config {a.config}: N={N} I={I} visible={int((nth > 0).sum())} tiles={bins.shape[0]} list len mean/max {ln.mean():.0f}/{ln.max():.0f}")
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        if name not in a.what.split(","):
+            continue
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{name}: {e0.elapsed_time(e1) / a.reps * 1000:.1f} us per call (pack + memsets + kernel)")
+
+
+if __name__ == "__main__":
+    main()
