@@ -64,6 +64,117 @@ __global__ void __launch_bounds__(256) tile_bin_edges_kernel(int m, const int64_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast binning used inside rasterize_gaussians (which only needs the per-tile id lists, not the 64-bit keys):
+// two-level sort.  (1) stable radix sort of the N Gaussians by depth bits (32-bit keys, ~2.4 MB of traffic),
+// (2) emit (tile id, Gaussian id) pairs in that order, (3) stable radix sort of the I pairs on the
+// ceil(log2 T) tile bits only (2 onesweep passes over 8-byte pairs instead of 6 over 12-byte pairs).
+// The result is IDENTICAL to sorting the reference's (tile << 32 | depth) keys stably: ties in (tile, depth)
+// stay in ascending Gaussian id, and the reference's phantom zero-key slots (see map_intersects_kernel) are
+// emitted first so they lead tile 0's list.
+__global__ void __launch_bounds__(256) depth_keys_kernel(int n, const float2 *__restrict__ xys,
+                                                         const float *__restrict__ depths,
+                                                         const int32_t *__restrict__ radii,
+                                                         const int32_t *__restrict__ tiles_hit, int tbx, int tby,
+                                                         float bw, uint32_t *__restrict__ keys,
+                                                         int32_t *__restrict__ vals, int32_t *__restrict__ emitted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = radii[i], reserved = tiles_hit[i];
+    int e = 0;
+    if (r > 0 && reserved > 0) {
+        const float2 c = xys[i];
+        int x0, y0, x1, y1;
+        tile_bbox(c.x, c.y, (float)r, tbx, tby, bw, x0, y0, x1, y1);
+        e = min(max(0, (x1 - x0) * (y1 - y0)), reserved);
+    }
+    emitted[i] = e;
+    keys[i] = e > 0 ? (uint32_t)__float_as_int(depths[i]) : 0xffffffffu;
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(256) gather_counts_kernel(int n, const int32_t *__restrict__ order,
+                                                            const int32_t *__restrict__ emitted,
+                                                            int32_t *__restrict__ emitted_sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) emitted_sorted[i] = emitted[order[i]];
+}
+
+// one warp per depth-sorted Gaussian; the first warps also zero-fill the phantom prefix
+__global__ void __launch_bounds__(256) emit_tiles_kernel(int n, int num_intersects,
+                                                         const int32_t *__restrict__ order,
+                                                         const int32_t *__restrict__ emitted_sorted,
+                                                         const int32_t *__restrict__ offs,  // exclusive scan
+                                                         const float2 *__restrict__ xys,
+                                                         const int32_t *__restrict__ radii, int tbx, int tby, float bw,
+                                                         uint32_t *__restrict__ tile_keys, int32_t *__restrict__ ids) {
+    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = gthread >> 5, lane = threadIdx.x & 31;
+    const int total_emitted = offs[n - 1] + emitted_sorted[n - 1];
+    const int phantoms = max(0, num_intersects - total_emitted);
+    for (int k = gthread; k < phantoms; k += gridDim.x * blockDim.x) {
+        tile_keys[k] = 0u;
+        ids[k] = 0;
+    }
+    if (warp >= n) return;
+    const int cnt = emitted_sorted[warp];
+    if (cnt <= 0) return;
+    const int g = order[warp];
+    const float2 c = xys[g];
+    int x0, y0, x1, y1;
+    tile_bbox(c.x, c.y, (float)radii[g], tbx, tby, bw, x0, y0, x1, y1);
+    const int w = x1 - x0;
+    const int base = phantoms + offs[warp];
+    for (int k = lane; k < cnt; k += 32) {
+        const int dst = base + k;
+        if (dst < num_intersects) {
+            tile_keys[dst] = (uint32_t)((y0 + k / w) * tbx + (x0 + k % w));
+            ids[dst] = g;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) tile_bin_edges32_kernel(int m, const uint32_t *__restrict__ sorted,
+                                                               int2 *__restrict__ bins) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int cur = (int)sorted[i];
+    if (i == 0) bins[cur].x = 0;
+    if (i == m - 1) bins[cur].y = m;
+    if (i == 0) return;
+    const int prev = (int)sorted[i - 1];
+    if (prev != cur) {
+        bins[prev].y = i;
+        bins[cur].x = i;
+    }
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct BinTilesLayout {
+    size_t keys_a, keys_b, vals_a, vals_b, emitted, emitted_sorted, offs, tkeys_a, tkeys_b, ids_a, cub, cub_bytes, total;
+};
+
+static BinTilesLayout bin_tiles_layout(int n, int m) {
+    BinTilesLayout L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    L.keys_a = take(4 * (size_t)n); L.keys_b = take(4 * (size_t)n);
+    L.vals_a = take(4 * (size_t)n); L.vals_b = take(4 * (size_t)n);
+    L.emitted = take(4 * (size_t)n); L.emitted_sorted = take(4 * (size_t)n); L.offs = take(4 * (size_t)n);
+    L.tkeys_a = take(4 * (size_t)m); L.tkeys_b = take(4 * (size_t)m); L.ids_a = take(4 * (size_t)m);
+    size_t b1 = 0, b2 = 0, b3 = 0;
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32);
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, m > 0 ? m : 1, 0, 32);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, b3, (const int32_t *)nullptr, (int32_t *)nullptr, n);
+    L.cub_bytes = b1 > b2 ? (b1 > b3 ? b1 : b3) : (b2 > b3 ? b2 : b3);
+    L.cub = take(L.cub_bytes + 256);
+    L.total = off;
+    return L;
+}
+
 static int key_end_bit(int num_tiles) {
     int bits = 0;
     while ((1ll << bits) < (long long)num_tiles) ++bits;
@@ -81,7 +192,8 @@ extern "C" size_t b200_scan_temp_bytes(int num_points) {
 }
 
 extern "C" int b200_cumulative_intersects(int num_points, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit,
-                                          void *temp, size_t temp_bytes, int32_t *total_host_pinned, void *stream) {
+                                          void *temp, size_t temp_bytes, int32_t *total_host_pinned,
+                                          const int32_t *flag_dev, void *stream) {
     B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
     B200_REQUIRE(num_tiles_hit && cum_tiles_hit && temp, "null pointer");
     cudaStream_t st = as_stream(stream);
@@ -90,6 +202,8 @@ extern "C" int b200_cumulative_intersects(int num_points, const int32_t *num_til
     if (total_host_pinned)
         B200_CUDA(cudaMemcpyAsync(total_host_pinned, cum_tiles_hit + (num_points - 1), sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, st));
+    if (total_host_pinned && flag_dev)
+        B200_CUDA(cudaMemcpyAsync(total_host_pinned + 1, flag_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return B200_OK;
 }
 
@@ -143,6 +257,64 @@ extern "C" int b200_get_tile_bin_edges(int num_intersects, int num_tiles, const 
     B200_REQUIRE(isect_ids_sorted, "null pointer");
     tile_bin_edges_kernel<<<ceil_div(num_intersects, 256), 256, 0, st>>>(num_intersects, isect_ids_sorted,
                                                                         reinterpret_cast<int2 *>(tile_bins));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" size_t b200_bin_tiles_ws_bytes(int num_points, int num_intersects) {
+    return bin_tiles_layout(num_points > 0 ? num_points : 1, num_intersects > 0 ? num_intersects : 1).total;
+}
+
+extern "C" int b200_bin_tiles(int num_points, int num_intersects, const float *xys, const float *depths,
+                              const int32_t *radii, const int32_t *num_tiles_hit, unsigned tiles_x, unsigned tiles_y,
+                              unsigned block_width, void *ws, size_t ws_bytes, int32_t *gaussian_ids_sorted,
+                              int32_t *tile_bins, void *stream) {
+    B200_REQUIRE(num_points >= 1 && num_intersects >= 0, "bad sizes");
+    B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
+    B200_REQUIRE(tile_bins, "null pointer");
+    const int num_tiles = (int)(tiles_x * tiles_y);
+    B200_REQUIRE(num_tiles >= 1, "bad tile bounds");
+    cudaStream_t st = as_stream(stream);
+    B200_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, st));
+    if (num_intersects == 0) return B200_OK;
+    B200_REQUIRE(xys && depths && radii && num_tiles_hit && ws && gaussian_ids_sorted, "null pointer");
+    const BinTilesLayout L = bin_tiles_layout(num_points, num_intersects);
+    B200_REQUIRE(ws_bytes >= L.total, "workspace too small: %zu < %zu", ws_bytes, L.total);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "workspace must be 256-byte aligned");
+    char *base = static_cast<char *>(ws);
+    uint32_t *keys_a = (uint32_t *)(base + L.keys_a), *keys_b = (uint32_t *)(base + L.keys_b);
+    int32_t *vals_a = (int32_t *)(base + L.vals_a), *order = (int32_t *)(base + L.vals_b);
+    int32_t *emitted = (int32_t *)(base + L.emitted), *emitted_sorted = (int32_t *)(base + L.emitted_sorted);
+    int32_t *offs = (int32_t *)(base + L.offs);
+    uint32_t *tkeys_a = (uint32_t *)(base + L.tkeys_a), *tkeys_b = (uint32_t *)(base + L.tkeys_b);
+    int32_t *ids_a = (int32_t *)(base + L.ids_a);
+    void *cub_ws = base + L.cub;
+    size_t cub_bytes = L.cub_bytes + 256;
+    const int n = num_points, m = num_intersects;
+    const int tbx = (int)tiles_x, tby = (int)tiles_y;
+    const float bw = (float)block_width;
+
+    depth_keys_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, reinterpret_cast<const float2 *>(xys), depths, radii,
+                                                        num_tiles_hit, tbx, tby, bw, keys_a, vals_a, emitted);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, order, n, 0, 32, st));
+    count_launch(5);
+    gather_counts_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, emitted, emitted_sorted);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, emitted_sorted, offs, n, st));
+    count_launch(2);
+    {
+        const long long threads = 32ll * n;
+        emit_tiles_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(n, m, order, emitted_sorted, offs,
+                                                                        reinterpret_cast<const float2 *>(xys), radii, tbx,
+                                                                        tby, bw, tkeys_a, ids_a);
+        B200_LAUNCH_CHECK();
+    }
+    int bits = key_end_bit(num_tiles) - 32;
+    if (bits < 1) bits = 1;
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, tkeys_a, tkeys_b, ids_a, gaussian_ids_sorted, m, 0, bits, st));
+    count_launch(1 + (bits + 7) / 8);
+    tile_bin_edges32_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, tkeys_b, reinterpret_cast<int2 *>(tile_bins));
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

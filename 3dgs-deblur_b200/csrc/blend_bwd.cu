@@ -93,15 +93,15 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
         voa = p.v_out_alpha[pix];
     }
     const float bgdot = __ldg(p.background) * vo0 + __ldg(p.background + 1) * vo1 + __ldg(p.background + 2) * vo2;
-    float T[S], Kc[S], bdot[S];
+    float Tm[S], Kc[S], bdot[S];  // Tm = T / S
     int bin_final[S];
     int my_max = -1;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        T[s] = 1.f; Kc[s] = 0.f; bdot[s] = 0.f; bin_final[s] = -1;
+        Tm[s] = inv_s; Kc[s] = 0.f; bdot[s] = 0.f; bin_final[s] = -1;
         if (inside) {
             const float Tf = p.final_Ts[pix * S + s];
-            T[s] = Tf;
+            Tm[s] = Tf * inv_s;
             Kc[s] = Tf * inv_s * (voa - bgdot);
             bin_final[s] = min(p.final_idx[pix * S + s], range.y - 1);  // batches only cover [range.x, range.y)
             my_max = max(my_max, bin_final[s]);
@@ -186,21 +186,22 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
                         const float dy = A.y + tau[s] * A.w - py;
                         const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
                         if (sigma > cut || sigma < 0.f) continue;
-                        const float vis = __expf(-sigma);
-                        const float alpha = fminf(0.99f, Bq.w * vis);
+                        const float vis = exp_neg_approx(sigma);
+                        const float ov = Bq.w * vis;
+                        const float alpha = fminf(0.99f, ov);
                         if (alpha < 1.f / 255.f) continue;
                         any = true;
-                        const float ra = __frcp_rn(1.f - alpha);
-                        T[s] *= ra;
-                        const float Tm = T[s] * inv_s;
-                        const float fac = alpha * Tm;
-                        const float v_alpha = Tm * cdot + ra * (Kc[s] - bdot[s]);
+                        const float ra = rcp_approx(1.f - alpha);
+                        Tm[s] *= ra;  // T / S of backward.cu:294-296
+                        const float fac = alpha * Tm[s];
+                        const float v_alpha = Tm[s] * cdot + ra * (Kc[s] - bdot[s]);
                         bdot[s] += fac * cdot;
                         facsum += fac;
-                        const float v_sigma = -Bq.w * vis * v_alpha;
-                        sxx += v_sigma * dx * dx; sxy += v_sigma * dx * dy; syy += v_sigma * dy * dy;
-                        const float gx = v_sigma * (Bq.x * dx + Bq.y * dy);
-                        const float gy = v_sigma * (Bq.y * dx + Bq.z * dy);
+                        const float v_sigma = -ov * v_alpha;  // no zeroing when the clamp is active (backward.cu:317)
+                        const float u = v_sigma * dx, w = v_sigma * dy;
+                        sxx += u * dx; sxy += u * dy; syy += w * dy;
+                        const float gx = Bq.x * u + Bq.y * w;
+                        const float gy = Bq.y * u + Bq.z * w;
                         gxs += gx; gys += gy; gxa += fabsf(gx); gya += fabsf(gy);
                         pvx += gx * tau[s]; pvy += gy * tau[s];
                         vop += vis * v_alpha;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
                     const float tot = butterfly16(v, lane);
                     if (my_dst && tot != 0.f) {
                         const int gid = s_rec[st][k].id;
-                        atomicAdd(my_dst + (size_t)gid * my_stride, tot);
+                        atomicAdd(my_dst + (unsigned)gid * (unsigned)my_stride, tot);  // N * 3 < 2^32
                     }
                 }
             }

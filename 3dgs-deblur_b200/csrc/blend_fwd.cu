@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const Blen
                         const float dy = A.y + tau[s] * A.w - py;
                         const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
                         if (sigma > cut || sigma < 0.f) continue;  // alpha < 1/255 guaranteed above thr
-                        const float alpha = fminf(0.999f, Bq.w * __expf(-sigma));
+                        const float alpha = fminf(0.999f, Bq.w * exp_neg_approx(sigma));
                         if (alpha < 1.f / 255.f) continue;
                         const float next_T = T[s] * (1.f - alpha);
                         if (next_T <= 1e-4f) {  // forward.cu:421-427: this sample is done, entry not blended

@@ -123,6 +123,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
                  : "memory");
 }
 
+// exp(-x) and 1/x at the precision of the reference's fast-math build: `__expf` there is ex2.approx(x * log2e)
+// (forward.cu:416, backward.cu:274 under setup.py:76 --use_fast_math); spelled in PTX so no denormal fix-up or
+// IEEE rounding sequence is emitted around the MUFU.
+__device__ __forceinline__ float exp_neg_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * -1.4426950408889634f));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -47,6 +47,7 @@ __device__ __forceinline__ void stage_rows(float *s, const float *g, int base, i
 struct ProjFwdOut {
     float *cov3d, *xys, *depths, *pix_vels, *conics, *comp;
     int32_t *radii, *tiles_hit;
+    int32_t *quat_flag;  // optional: set to 1 if any |q| - 1 >= 1e-6 (the reference's Python-side assert, fused)
 };
 
 template <bool VEC>
@@ -63,6 +64,11 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_forward_kernel(ProjCommo
     const int t = threadIdx.x;
     if (t >= count) return;
     const int idx = base + t;
+
+    if (o.quat_flag) {  // project_gaussians.py:69: assert (quats.norm(dim=-1) - 1 < 1e-6).all()
+        const float qw = s_quats[4 * t], qx = s_quats[4 * t + 1], qy = s_quats[4 * t + 2], qz = s_quats[4 * t + 3];
+        if (!(sqrtf(qw * qw + qx * qx + qy * qy + qz * qz) - 1.f < 1e-6f)) atomicOr(o.quat_flag, 1);
+    }
 
     float vm[12];
 #pragma unroll
@@ -430,13 +436,13 @@ extern "C" int b200_project_gaussians_forward(int num_points, const float *means
                                               unsigned img_height, unsigned img_width, unsigned block_width,
                                               float clip_thresh, float *cov3d, float *xys, float *depths,
                                               float *pix_vels, int32_t *radii, float *conics, float *compensation,
-                                              int32_t *num_tiles_hit, void *stream) {
+                                              int32_t *num_tiles_hit, int32_t *quat_norm_flag, void *stream) {
     ProjCommon p;
     int rc = fill_common(p, num_points, means3d, scales, glob_scale, quats, lin_vel, ang_vel, rolling_shutter_time,
                          exposure_time, viewmat, fx, fy, cx, cy, img_height, img_width, block_width, clip_thresh);
     if (rc) return rc;
     B200_REQUIRE(cov3d && xys && depths && pix_vels && radii && conics && compensation && num_tiles_hit, "null output pointer");
-    ProjFwdOut o{cov3d, xys, depths, pix_vels, conics, compensation, radii, num_tiles_hit};
+    ProjFwdOut o{cov3d, xys, depths, pix_vels, conics, compensation, radii, num_tiles_hit, quat_norm_flag};
     const int blocks = ceil_div(num_points, PROJ_THREADS);
     const bool vec = aligned16(means3d) && aligned16(scales) && aligned16(quats);
     if (vec) project_forward_kernel<true><<<blocks, PROJ_THREADS, 0, as_stream(stream)>>>(p, o);

@@ -40,7 +40,7 @@ def num_sh_bases(degree):
 
 def project_gaussians_forward(num_points, means3d, scales, glob_scale, quats, linear_velocity, angular_velocity,
                               rolling_shutter_time, exposure_time, viewmat, fx, fy, cx, cy, img_height, img_width,
-                              block_width, clip_thresh, _vel_tensors=None):
+                              block_width, clip_thresh, _vel_tensors=None, _quat_flag=None):
     """-> (cov3d, xys, depths, pix_vels, radii, conics, compensation, num_tiles_hit)  [bindings.cu:154-257]"""
     require_cuda(means3d, scales, quats, viewmat)
     dev = means3d.device
@@ -61,7 +61,8 @@ def project_gaussians_forward(num_points, means3d, scales, glob_scale, quats, li
             n, ptr(_f32(means3d)), ptr(_f32(scales)), float(glob_scale), ptr(_f32(quats)), ptr(lin), ptr(ang),
             float(rolling_shutter_time), float(exposure_time), ptr(_f32(viewmat)), float(fx), float(fy), float(cx),
             float(cy), int(img_height), int(img_width), int(block_width), float(clip_thresh),
-            ptr(cov3d), ptr(xys), ptr(depths), ptr(pix_vels), ptr(radii), ptr(conics), ptr(comp), ptr(tiles), stream()))
+            ptr(cov3d), ptr(xys), ptr(depths), ptr(pix_vels), ptr(radii), ptr(conics), ptr(comp), ptr(tiles),
+            ptr(_quat_flag), stream()))
     return cov3d, xys, depths, pix_vels, radii, conics, comp, tiles
 
 
@@ -198,10 +199,34 @@ def cumulative_intersects(num_tiles_hit):
         cum = torch.empty((n,), dtype=torch.int32, device=dev)
         nbytes = lib.b200_scan_temp_bytes(n)
         temp = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
-        total = torch.empty((1,), dtype=torch.int32, pin_memory=True)
-        check(lib.b200_cumulative_intersects(n, ptr(num_tiles_hit), ptr(cum), ptr(temp), nbytes, total.data_ptr(), stream()))
+        host = _lib.host_scratch(dev)
+        flag = _lib.take_pending_flag(dev)
+        check(lib.b200_cumulative_intersects(n, ptr(num_tiles_hit), ptr(cum), ptr(temp), nbytes, host.data_ptr(),
+                                             ptr(flag), stream()))
         torch.cuda.current_stream().synchronize()  # the one host sync of the path (utils.py:124 `.item()`)
-    return int(total[0]), cum
+        total = int(host[0])
+        if flag is not None and int(host[1]) != 0:
+            raise AssertionError("quats must be normalized")  # deferred project_gaussians.py:69
+    return total, cum
+
+
+def bin_tiles(num_intersects, xys, depths, radii, num_tiles_hit, tile_bounds, block_width):
+    """Extension: fused two-level binning -> (gaussian_ids_sorted (I,) i32, tile_bins (tiles,2) i32); identical to
+    bin_and_sort_gaussians()[3:5] (utils.py:128-182) without materialising the 64-bit keys."""
+    require_cuda(xys, depths, radii, num_tiles_hit)
+    dev = xys.device
+    with torch.cuda.device(dev):
+        lib = _lib.load()
+        n, m = xys.size(0), int(num_intersects)
+        tiles = int(tile_bounds[0]) * int(tile_bounds[1])
+        ids = torch.empty((m,), dtype=torch.int32, device=dev)
+        bins = torch.empty((tiles, 2), dtype=torch.int32, device=dev)
+        nbytes = lib.b200_bin_tiles_ws_bytes(n, m)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        check(lib.b200_bin_tiles(n, m, ptr(_f32(xys)), ptr(_f32(depths)), ptr(radii), ptr(num_tiles_hit),
+                                 int(tile_bounds[0]), int(tile_bounds[1]), int(block_width), ptr(ws), nbytes, ptr(ids),
+                                 ptr(bins), stream()))
+    return ids, bins
 
 
 def _geom(tile_bounds, block, img_size):

@@ -15,6 +15,7 @@ from torch import Tensor
 from torch.autograd import Function
 
 import gsplat.cuda as _C
+from gsplat import _lib
 
 
 def project_gaussians(
@@ -41,7 +42,8 @@ def project_gaussians(
     means3d (N,3); scales (N,3) (already exp'd); quats (N,4) normalised wxyz; linear/angular velocity
     (3,) or (1,3) in camera coordinates or None; viewmat (3,4) or (4,4) world-to-camera, row major."""
     assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
-    assert (quats.norm(dim=-1) - 1 < 1e-6).all(), "quats must be normalized"
+    if _lib.SYNC_CHECKS or not quats.is_cuda:
+        assert (quats.norm(dim=-1) - 1 < 1e-6).all(), "quats must be normalized"
 
     if linear_velocity is None:
         assert angular_velocity is None
@@ -72,9 +74,12 @@ class _ProjectGaussians(Function):
             raise ValueError(f"Invalid shape for means3d: {means3d.shape}")
         dev = means3d.device
         lin, ang = _vel_dev(linear_velocity, dev), _vel_dev(angular_velocity, dev)
+        # the normalisation assert of project_gaussians.py:69 is evaluated inside the kernel and raised at the next
+        # host sync of the path (the intersection-count read-back in rasterize_gaussians); see gsplat/_lib.py
+        flag = None if _lib.SYNC_CHECKS else _lib.new_quat_flag(dev)
         (cov3d, xys, depths, pix_vels, radii, conics, compensation, num_tiles_hit) = _C.project_gaussians_forward(
             num_points, means3d, scales, glob_scale, quats, None, None, rolling_shutter_time, exposure_time, viewmat,
-            fx, fy, cx, cy, img_height, img_width, block_width, clip_thresh, _vel_tensors=(lin, ang))
+            fx, fy, cx, cy, img_height, img_width, block_width, clip_thresh, _vel_tensors=(lin, ang), _quat_flag=flag)
 
         ctx.cfg = (num_points, glob_scale, fx, fy, cx, cy, img_height, img_width, rolling_shutter_time, exposure_time)
         ctx.vel_shapes = (linear_velocity.shape, angular_velocity.shape)

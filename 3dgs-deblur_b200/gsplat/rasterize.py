@@ -8,7 +8,7 @@ from torch.autograd import Function
 
 import gsplat.cuda as _C
 
-from .utils import bin_and_sort_gaussians, compute_cumulative_intersects
+from .utils import compute_cumulative_intersects
 
 
 def rasterize_gaussians(
@@ -70,8 +70,10 @@ class _RasterizeGaussians(Function):
             final_Ts = torch.zeros(img_height, img_width, blur_samples, device=xys.device)
             final_idx = torch.zeros(img_height, img_width, blur_samples, device=xys.device)
         else:
-            (_, _, _, gaussian_ids_sorted, tile_bins) = bin_and_sort_gaussians(
-                num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width)
+            # only the per-tile id lists are consumed below, so the fused two-level binning is used; it yields the
+            # same gaussian_ids_sorted / tile_bins as bin_and_sort_gaussians(...)[3:5] (tests/test_gpu_parity.py)
+            gaussian_ids_sorted, tile_bins = _C.bin_tiles(num_intersects, xys, depths, radii, num_tiles_hit,
+                                                          tile_bounds, block_width)
             rasterize_fn = _C.rasterize_forward if colors.shape[-1] == 3 else _C.nd_rasterize_forward
             out_img, final_Ts, final_idx = rasterize_fn(
                 tile_bounds, block, img_size, blur_samples, gaussian_ids_sorted, tile_bins, xys, pix_vels,

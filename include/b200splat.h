@@ -62,14 +62,16 @@ B200_API size_t b200_packed_record_bytes(void);
  * forward.cu:13-112).  lin_vel / ang_vel are DEVICE float[3] (NULL = zero) so the caller never
  * needs the .tolist() D2H sync of project_gaussians.py:178-179.  viewmat: >= 12 floats row-major.
  * Outputs: cov3d (N,6) xys (N,2) depths (N) pix_vels (N,2) radii (N) i32 conics (N,3)
- * compensation (N) num_tiles_hit (N) i32. */
+ * compensation (N) num_tiles_hit (N) i32.  quat_norm_flag (optional DEVICE int32, caller-zeroed) is OR-ed with 1 if
+ * any quaternion violates the reference's `quats.norm(dim=-1) - 1 < 1e-6` assert (project_gaussians.py:69), so the
+ * caller can raise it at its next host sync instead of paying a separate reduction + sync. */
 B200_API int b200_project_gaussians_forward(int num_points, const float *means3d, const float *scales, float glob_scale,
                                    const float *quats, const float *lin_vel, const float *ang_vel,
                                    float rolling_shutter_time, float exposure_time, const float *viewmat, float fx,
                                    float fy, float cx, float cy, unsigned img_height, unsigned img_width,
                                    unsigned block_width, float clip_thresh, float *cov3d, float *xys, float *depths,
                                    float *pix_vels, int32_t *radii, float *conics, float *compensation,
-                                   int32_t *num_tiles_hit, void *stream);
+                                   int32_t *num_tiles_hit, int32_t *quat_norm_flag, void *stream);
 
 /* replaces project_gaussians_backward_tensor (bindings.h:74-108, bindings.cu:259-358; kernel
  * backward.cu:371-451) AND the Python-side v_viewmat block (project_gaussians.py:272-307) AND adds
@@ -104,10 +106,12 @@ B200_API int b200_compute_sh_backward(int method, int num_points, int degree, in
 /* ---- tile binning -----------------------------------------------------------------------
  * b200_cumulative_intersects replaces torch.cumsum in compute_cumulative_intersects
  * (gsplat/utils.py:106-125): inclusive int32 scan.  `total_host_pinned` (HOST, optional) receives
- * cum[N-1] by an async copy on `stream` (the caller synchronises before reading it). */
+ * cum[N-1] by an async copy on `stream` (the caller synchronises before reading it); when `flag_dev` is given its
+ * int32 is copied to total_host_pinned[1] in the same way (deferred quat-norm check, see above). */
 B200_API size_t b200_scan_temp_bytes(int num_points);
 B200_API int b200_cumulative_intersects(int num_points, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit, void *temp,
-                               size_t temp_bytes, int32_t *total_host_pinned, void *stream);
+                                        size_t temp_bytes, int32_t *total_host_pinned, const int32_t *flag_dev,
+                                        void *stream);
 
 /* replaces map_gaussian_to_intersects_tensor (bindings.h:199-209, bindings.cu:360-402; kernel
  * forward.cu:116-153).  Slots reserved by cum_tiles_hit but not emitted (the reference's "phantom"
@@ -128,6 +132,17 @@ B200_API int b200_sort_intersects(int num_intersects, int num_tiles, const int64
  * tile_bins (num_tiles,2) i32, (0,0) for empty tiles. */
 B200_API int b200_get_tile_bin_edges(int num_intersects, int num_tiles, const int64_t *isect_ids_sorted, int32_t *tile_bins,
                             void *stream);
+
+/* Fused fast path of bin_and_sort_gaussians for callers that only need what the blend consumes
+ * (rasterize.py:146-163 discards the key arrays): gaussian_ids_sorted (I) and tile_bins (num_tiles,2), produced by a
+ * two-level sort (Gaussians by depth, then pairs by tile id) that is order-identical to the stable sort of the
+ * reference's 64-bit keys, phantom zero-key slots included.  `ws`: 256-byte aligned scratch of
+ * b200_bin_tiles_ws_bytes(N, I) bytes.  num_intersects must equal sum(num_tiles_hit). */
+B200_API size_t b200_bin_tiles_ws_bytes(int num_points, int num_intersects);
+B200_API int b200_bin_tiles(int num_points, int num_intersects, const float *xys, const float *depths,
+                            const int32_t *radii, const int32_t *num_tiles_hit, unsigned tiles_x, unsigned tiles_y,
+                            unsigned block_width, void *ws, size_t ws_bytes, int32_t *gaussian_ids_sorted,
+                            int32_t *tile_bins, void *stream);
 
 /* ---- blend (blur + rolling shutter), 3 channels ------------------------------------------
  * replaces rasterize_forward_tensor (bindings.h:110-127, bindings.cu:424-503; kernel forward.cu:306-456).

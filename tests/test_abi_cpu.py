@@ -51,7 +51,7 @@ def test_argument_errors_are_reported_before_any_gpu_work(lib):
     rc = lib.b200_rasterize_forward(10, 8, 8, 16, 11, *([None] * 4), 0.0, 0.0, *([None] * 9))
     assert rc == -1 and b"unsupported blur size" in lib.b200_last_error()
     rc = lib.b200_project_gaussians_forward(0, None, None, 1.0, None, None, None, 0.0, 0.0, None, 1.0, 1.0, 0.0, 0.0, 8, 8,
-                                            16, 0.01, *([None] * 9))
+                                            16, 0.01, *([None] * 10))
     assert rc == -1 and b"num_points" in lib.b200_last_error()
     rc = lib.b200_compute_sh_forward(7, 4, 3, 3, None, None, None, None)
     assert rc == -1 and b"Invalid method" in lib.b200_last_error()

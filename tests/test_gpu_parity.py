@@ -239,6 +239,22 @@ def test_binning_bit_exact_vs_oracle(name, n, motion):
         assert (b["isect_ids"] == 0).sum() > 0  # the blur-inflated float radius really produces phantom slots
 
 
+@pytest.mark.parametrize("name,n,motion,H,W,bw", [("c1", None, False, None, None, 16), ("c2", 30000, True, None, None, 16),
+                                                   ("c2", None, True, None, None, 16), ("c2", 5000, True, 40, 56, 8),
+                                                   ("c1", 3000, False, 9, 7, 16), ("c4", 60000, True, None, None, 16)])
+def test_fused_two_level_binning_is_order_identical(name, n, motion, H, W, bw):
+    """gsplat.cuda.bin_tiles (depth sort, emit, tile sort) == stable sort of the reference's 64-bit keys, phantom
+    slots included: gaussian_ids_sorted and tile_bins bit for bit."""
+    d = scene_np(name, n=n, motion=motion, H=H, W=W)
+    d["bw"] = bw
+    o = oracle_project(d)
+    b = O.bin_and_sort(o["xys"], o["depths"], o["radii"], o["num_tiles_hit"], d["H"], d["W"], bw)
+    tb = ((d["W"] + bw - 1) // bw, (d["H"] + bw - 1) // bw, 1)
+    ids, bins = _C.bin_tiles(b["num_intersects"], cu(o["xys"]), cu(o["depths"]), cu(o["radii"]), cu(o["num_tiles_hit"]), tb, bw)
+    assert np.array_equal(bins.cpu().numpy(), b["tile_bins"])
+    assert np.array_equal(ids.cpu().numpy(), b["gaussian_ids_sorted"])
+
+
 def test_map_and_bins_golden_reference(golden):
     g = golden("map_bins.npz")
     H, W, bw = int(g["H"]), int(g["W"]), int(g["bw"])
@@ -397,8 +413,23 @@ def test_empty_and_error_paths():
     assert torch.allclose(img, bg.expand_as(img)) and (alpha == 1).all()
     with pytest.raises(AssertionError):
         project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]), None, None, 0, 0, cu(vm), 1, 1, 0, 0, 8, 8, 17)
-    with pytest.raises(AssertionError):
-        project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]) * 2, None, None, 0, 0, cu(vm), 1, 1, 0, 0, 8, 8, 16)
+    # un-normalised quaternions: the reference asserts inside project_gaussians (project_gaussians.py:69); here the
+    # kernel raises a device flag and the same AssertionError surfaces at the next host sync of the path
+    bad = project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]) * 2, None, None, 0, 0, cu(d["viewmat"]),
+                            d["fx"], d["fy"], d["cx"], d["cy"], d["H"], d["W"], 16)
+    with pytest.raises(AssertionError, match="quats must be normalized"):
+        gsplat.compute_cumulative_intersects(bad[6])
+    from gsplat import _lib
+    _lib.SYNC_CHECKS = True
+    try:
+        with pytest.raises(AssertionError, match="quats must be normalized"):
+            project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]) * 2, None, None, 0, 0, cu(vm), 1, 1, 0, 0, 8, 8, 16)
+    finally:
+        _lib.SYNC_CHECKS = False
+    # a shorter-than-unit quaternion passes, exactly like the reference's one-sided check
+    ok = project_gaussians(cu(d["means"]), cu(d["scales"]), 1.0, cu(d["quats"]) * 0.5, None, None, 0, 0, cu(d["viewmat"]),
+                           d["fx"], d["fy"], d["cx"], d["cy"], d["H"], d["W"], 16)
+    gsplat.compute_cumulative_intersects(ok[6])
     with pytest.raises(RuntimeError, match="unsupported blur size"):
         rasterize_gaussians(xys, depths, pix_vels, radii + 1, conics, nth + 1, cu(oracle_colors(d)), cu(d["opacity"]),
                             d["H"], d["W"], 16, exposure_time=0.1, blur_samples=11)
