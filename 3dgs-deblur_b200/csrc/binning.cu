@@ -4,7 +4,7 @@
 // primitives restricted to the key bits that can be set instead of a generic 64-bit torch.sort + gather.
 #include <cub/cub.cuh>
 
-#include "common.cuh"
+#include "blend_common.cuh"
 
 namespace b200 {
 
@@ -175,6 +175,104 @@ static BinTilesLayout bin_tiles_layout(int n, int m) {
     return L;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Culled binning (the path rasterize_gaussians uses): like the two-level sort above, but a (tile, Gaussian) pair
+// of the reference's bbox is only kept if the Gaussian can reach alpha >= 1/255 somewhere in that tile for some
+// blur sample (may_touch_rect on the packed record).  The reference's bbox is the square around a 3-sigma CIRCLE
+// inflated isotropically by the blur length (forward.cu:63-102), so thin, faint or fast-moving splats reserve many
+// tiles they never colour: 76 % of the 2.45 M pairs of BASELINE config 2 are dropped here.  Dropped pairs cannot
+// change any pixel (same argument as the per-warp cull), the survivors keep the reference's order, and the
+// reference's phantom copies of Gaussian 0 in tile 0 survive exactly when Gaussian 0 can touch tile 0.
+struct CullGeom {
+    int H, W, bw, tbx, tby, S;
+    float rs_time, exposure;
+};
+
+__device__ __forceinline__ bool tile_survives(const PackedGaussian &g, int tx, int ty, const CullGeom &c) {
+    const float x0 = (float)(tx * c.bw) + 0.5f, x1 = (float)min(c.W, (tx + 1) * c.bw) - 0.5f;
+    const float y0 = (float)(ty * c.bw) + 0.5f, y1 = (float)min(c.H, (ty + 1) * c.bw) - 0.5f;
+    const float ra = (float)((double)c.rs_time * ((double)(y0 / (float)c.H) - 0.5));
+    const float rb = (float)((double)c.rs_time * ((double)(y1 / (float)c.H) - 0.5));
+    return may_touch_rect(g, x0, x1, y0, y1, fminf(ra, rb), fmaxf(ra, rb), c.exposure, c.S);
+}
+
+// counters: [0] = sum of reserved slots (the reference's num_intersects), [1] = phantom slots,
+//           [2] = 1 if Gaussian 0 can touch tile 0, [3] = number of list entries after culling (filled later)
+__global__ void __launch_bounds__(256) cull_count_kernel(int n, const PackedGaussian *__restrict__ rec,
+                                                         const float *__restrict__ depths,
+                                                         const int32_t *__restrict__ radii,
+                                                         const int32_t *__restrict__ tiles_hit, CullGeom c,
+                                                         uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
+                                                         int32_t *__restrict__ survivors, int32_t *__restrict__ counters) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const int g = warp;
+    const int r = radii[g], reserved = tiles_hit[g];
+    int kept = 0, emitted_ref = 0;
+    if (r > 0 && reserved > 0) {
+        const PackedGaussian pg = rec[g];
+        int x0, y0, x1, y1;
+        tile_bbox(pg.x, pg.y, (float)r, c.tbx, c.tby, (float)c.bw, x0, y0, x1, y1);
+        const int w = x1 - x0;
+        emitted_ref = min(max(0, w * (y1 - y0)), reserved);
+        for (int k = lane; k < emitted_ref; k += 32) kept += tile_survives(pg, x0 + k % w, y0 + k / w, c) ? 1 : 0;
+        kept = __reduce_add_sync(0xffffffffu, kept);
+    }
+    if (lane == 0) {
+        survivors[g] = kept;
+        keys[g] = kept > 0 ? (uint32_t)__float_as_int(depths[g]) : 0xffffffffu;
+        vals[g] = g;
+        if (reserved > 0) atomicAdd(counters + 0, reserved);
+        if (reserved - emitted_ref > 0) atomicAdd(counters + 1, reserved - emitted_ref);
+        if (g == 0) counters[2] = tile_survives(rec[0], 0, 0, c) ? 1 : 0;
+    }
+}
+
+__global__ void cull_total_kernel(int n, const int32_t *__restrict__ offs, const int32_t *__restrict__ surv_sorted,
+                                  int32_t *__restrict__ counters) {
+    const int phantoms = counters[2] ? counters[1] : 0;
+    counters[3] = phantoms + offs[n - 1] + surv_sorted[n - 1];
+}
+
+__global__ void __launch_bounds__(256) cull_emit_kernel(int n, int total, const int32_t *__restrict__ order,
+                                                        const int32_t *__restrict__ surv_sorted,
+                                                        const int32_t *__restrict__ offs,
+                                                        const PackedGaussian *__restrict__ rec,
+                                                        const int32_t *__restrict__ radii,
+                                                        const int32_t *__restrict__ tiles_hit, CullGeom c,
+                                                        const int32_t *__restrict__ counters,
+                                                        uint32_t *__restrict__ tile_keys, int32_t *__restrict__ ids) {
+    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = gthread >> 5, lane = threadIdx.x & 31;
+    const int phantoms = counters[2] ? counters[1] : 0;
+    for (int k = gthread; k < min(phantoms, total); k += gridDim.x * blockDim.x) {
+        tile_keys[k] = 0u;
+        ids[k] = 0;
+    }
+    if (warp >= n) return;
+    if (surv_sorted[warp] <= 0) return;
+    const int g = order[warp];
+    const PackedGaussian pg = rec[g];
+    int x0, y0, x1, y1;
+    tile_bbox(pg.x, pg.y, (float)radii[g], c.tbx, c.tby, (float)c.bw, x0, y0, x1, y1);
+    const int w = x1 - x0;
+    const int emitted_ref = min(max(0, w * (y1 - y0)), tiles_hit[g]);
+    int base = phantoms + offs[warp];
+    for (int k0 = 0; k0 < emitted_ref; k0 += 32) {
+        const int k = k0 + lane;
+        const bool keep = k < emitted_ref && tile_survives(pg, x0 + k % w, y0 + k / w, c);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int dst = base + __popc(m & ((1u << lane) - 1u));
+            if (dst < total) {
+                tile_keys[dst] = (uint32_t)((y0 + k / w) * c.tbx + (x0 + k % w));
+                ids[dst] = g;
+            }
+        }
+        base += __popc(m);
+    }
+}
+
 static int key_end_bit(int num_tiles) {
     int bits = 0;
     while ((1ll << bits) < (long long)num_tiles) ++bits;
@@ -310,6 +408,136 @@ extern "C" int b200_bin_tiles(int num_points, int num_intersects, const float *x
                                                                         tby, bw, tkeys_a, ids_a);
         B200_LAUNCH_CHECK();
     }
+    int bits = key_end_bit(num_tiles) - 32;
+    if (bits < 1) bits = 1;
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, tkeys_a, tkeys_b, ids_a, gaussian_ids_sorted, m, 0, bits, st));
+    count_launch(1 + (bits + 7) / 8);
+    tile_bin_edges32_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, tkeys_b, reinterpret_cast<int2 *>(tile_bins));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// ---- culled binning entry points ---------------------------------------------------------------------------
+// Two workspaces: a per-Gaussian one (size known up front) that carries {order, survivors, offsets, counters} from
+// the count phase to the emit phase, and a per-entry one sized after the host has read the culled entry count.
+struct CullWsG {
+    size_t keys_a, keys_b, vals_a, order, survivors, surv_sorted, offs, counters, cub, cub_bytes, total;
+};
+static CullWsG cull_ws_g(int n) {
+    CullWsG L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    L.keys_a = take(4 * (size_t)n); L.keys_b = take(4 * (size_t)n); L.vals_a = take(4 * (size_t)n);
+    L.order = take(4 * (size_t)n); L.survivors = take(4 * (size_t)n); L.surv_sorted = take(4 * (size_t)n);
+    L.offs = take(4 * (size_t)n); L.counters = take(256);
+    size_t b1 = 0, b3 = 0;
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, b3, (const int32_t *)nullptr, (int32_t *)nullptr, n);
+    L.cub_bytes = (b1 > b3 ? b1 : b3) + 256;
+    L.cub = take(L.cub_bytes);
+    L.total = off;
+    return L;
+}
+struct CullWsE {
+    size_t tkeys_a, tkeys_b, ids_a, cub, cub_bytes, total;
+};
+static CullWsE cull_ws_e(int m) {
+    CullWsE L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    L.tkeys_a = take(4 * (size_t)m); L.tkeys_b = take(4 * (size_t)m); L.ids_a = take(4 * (size_t)m);
+    size_t b2 = 0;
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, m, 0, 32);
+    L.cub_bytes = b2 + 256;
+    L.cub = take(L.cub_bytes);
+    L.total = off;
+    return L;
+}
+
+extern "C" size_t b200_bin_cull_ws_bytes(int num_points) { return cull_ws_g(num_points > 0 ? num_points : 1).total; }
+extern "C" size_t b200_bin_cull_emit_ws_bytes(int num_entries) { return cull_ws_e(num_entries > 0 ? num_entries : 1).total; }
+
+static CullGeom make_cull_geom(unsigned H, unsigned W, unsigned bw, unsigned S, float rs, float exposure) {
+    CullGeom c;
+    c.H = (int)H; c.W = (int)W; c.bw = (int)bw; c.tbx = (int)((W + bw - 1) / bw); c.tby = (int)((H + bw - 1) / bw);
+    c.S = (int)S; c.rs_time = rs; c.exposure = exposure;
+    return c;
+}
+
+extern "C" int b200_bin_cull_count(int num_points, const void *packed, const float *depths, const int32_t *radii,
+                                   const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
+                                   unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
+                                   float exposure_time, void *ws_g, size_t ws_g_bytes, int32_t *totals_host_pinned,
+                                   void *stream) {
+    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
+    B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
+    B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");
+    B200_REQUIRE(packed && depths && radii && num_tiles_hit && ws_g && totals_host_pinned, "null pointer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ws_g) & 255u) == 0, "workspace must be 256-byte aligned");
+    const int n = num_points;
+    const CullWsG L = cull_ws_g(n);
+    B200_REQUIRE(ws_g_bytes >= L.total, "workspace too small: %zu < %zu", ws_g_bytes, L.total);
+    char *base = static_cast<char *>(ws_g);
+    uint32_t *keys_a = (uint32_t *)(base + L.keys_a), *keys_b = (uint32_t *)(base + L.keys_b);
+    int32_t *vals_a = (int32_t *)(base + L.vals_a), *order = (int32_t *)(base + L.order);
+    int32_t *survivors = (int32_t *)(base + L.survivors), *surv_sorted = (int32_t *)(base + L.surv_sorted);
+    int32_t *offs = (int32_t *)(base + L.offs), *counters = (int32_t *)(base + L.counters);
+    void *cub_ws = base + L.cub;
+    size_t cub_bytes = L.cub_bytes;
+    cudaStream_t st = as_stream(stream);
+    const CullGeom c = make_cull_geom(img_height, img_width, block_width, n_blur_samples, rolling_shutter_time, exposure_time);
+    B200_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+    const long long threads = 32ll * n;
+    cull_count_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(n, reinterpret_cast<const PackedGaussian *>(packed),
+                                                                    depths, radii, num_tiles_hit, c, keys_a, vals_a,
+                                                                    survivors, counters);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, order, n, 0, 32, st));
+    count_launch(5);
+    gather_counts_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, survivors, surv_sorted);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, surv_sorted, offs, n, st));
+    count_launch(2);
+    cull_total_kernel<<<1, 1, 0, st>>>(n, offs, surv_sorted, counters);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(totals_host_pinned, counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return B200_OK;
+}
+
+extern "C" int b200_bin_cull_emit(int num_points, int num_entries, const void *packed, const int32_t *radii,
+                                  const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
+                                  unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
+                                  float exposure_time, const void *ws_g, void *ws_e, size_t ws_e_bytes,
+                                  int32_t *gaussian_ids_sorted, int32_t *tile_bins, void *stream) {
+    B200_REQUIRE(num_points >= 1 && num_entries >= 0, "bad sizes");
+    B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
+    B200_REQUIRE(tile_bins && ws_g, "null pointer");
+    const CullGeom c = make_cull_geom(img_height, img_width, block_width, n_blur_samples, rolling_shutter_time, exposure_time);
+    const int num_tiles = c.tbx * c.tby;
+    cudaStream_t st = as_stream(stream);
+    B200_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, st));
+    if (num_entries == 0) return B200_OK;
+    B200_REQUIRE(packed && radii && num_tiles_hit && gaussian_ids_sorted && ws_e, "null pointer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ws_e) & 255u) == 0, "workspace must be 256-byte aligned");
+    const int n = num_points, m = num_entries;
+    const CullWsG G = cull_ws_g(n);
+    const CullWsE E = cull_ws_e(m);
+    B200_REQUIRE(ws_e_bytes >= E.total, "workspace too small: %zu < %zu", ws_e_bytes, E.total);
+    const char *gb = static_cast<const char *>(ws_g);
+    const int32_t *order = (const int32_t *)(gb + G.order), *surv_sorted = (const int32_t *)(gb + G.surv_sorted);
+    const int32_t *offs = (const int32_t *)(gb + G.offs), *counters = (const int32_t *)(gb + G.counters);
+    char *eb = static_cast<char *>(ws_e);
+    uint32_t *tkeys_a = (uint32_t *)(eb + E.tkeys_a), *tkeys_b = (uint32_t *)(eb + E.tkeys_b);
+    int32_t *ids_a = (int32_t *)(eb + E.ids_a);
+    void *cub_ws = eb + E.cub;
+    size_t cub_bytes = E.cub_bytes;
+    const long long threads = 32ll * n;
+    cull_emit_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(n, m, order, surv_sorted, offs,
+                                                                   reinterpret_cast<const PackedGaussian *>(packed), radii,
+                                                                   num_tiles_hit, c, counters, tkeys_a, ids_a);
+    B200_LAUNCH_CHECK();
     int bits = key_end_bit(num_tiles) - 32;
     if (bits < 1) bits = 1;
     B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, tkeys_a, tkeys_b, ids_a, gaussian_ids_sorted, m, 0, bits, st));

@@ -232,25 +232,19 @@ static int launch_bwd(const BlendBwdParams &p, cudaStream_t st) {
 
 using namespace b200;
 
-extern "C" int b200_rasterize_backward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
-                                       unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
-                                       const int32_t *tile_bins, const float *xys, const float *pix_vels,
-                                       float rolling_shutter_time, float exposure_time, const float *conics,
-                                       const float *colors, const float *opacities, const float *background,
-                                       const float *final_Ts, const int32_t *final_idx, const float *v_output,
-                                       const float *v_output_alpha, void *packed_ws, float *v_xy, float *v_xy_abs,
-                                       float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity,
-                                       void *stream) {
+static int run_blend_backward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                              unsigned n_blur_samples, const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                              const void *packed, float rolling_shutter_time, float exposure_time,
+                              const float *background, const float *final_Ts, const int32_t *final_idx,
+                              const float *v_output, const float *v_output_alpha, float *v_xy, float *v_xy_abs,
+                              float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity, cudaStream_t st) {
     B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");
     B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
     B200_REQUIRE(img_height > 0 && img_width > 0, "image size must be positive");
-    B200_REQUIRE(gaussian_ids_sorted && tile_bins && xys && pix_vels && conics && colors && opacities && background,
-                 "null input pointer");
+    B200_REQUIRE(tile_bins && background && packed && aligned16(packed), "null / misaligned input pointer");
     B200_REQUIRE(final_Ts && final_idx && v_output && v_output_alpha, "null saved / cotangent pointer");
-    B200_REQUIRE(packed_ws && aligned16(packed_ws), "packed_ws must be a 16-byte aligned scratch buffer");
     B200_REQUIRE(v_xy && v_xy_abs && v_pix_vels && v_conic && v_colors && v_opacity, "null output pointer");
-    cudaStream_t st = as_stream(stream);
     const size_t n = (size_t)num_points;
     B200_CUDA(cudaMemsetAsync(v_xy, 0, n * 2 * sizeof(float), st));
     B200_CUDA(cudaMemsetAsync(v_xy_abs, 0, n * 2 * sizeof(float), st));
@@ -258,15 +252,13 @@ extern "C" int b200_rasterize_backward(int num_points, unsigned img_height, unsi
     B200_CUDA(cudaMemsetAsync(v_conic, 0, n * 3 * sizeof(float), st));
     B200_CUDA(cudaMemsetAsync(v_colors, 0, n * 3 * sizeof(float), st));
     B200_CUDA(cudaMemsetAsync(v_opacity, 0, n * sizeof(float), st));
-    int rc = launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed_ws, st);
-    if (rc) return rc;
     BlendBwdParams p;
     p.g = BlendGeom{(int)img_height, (int)img_width, (int)block_width,
                     (int)((img_width + block_width - 1) / block_width),
                     (int)((img_height + block_width - 1) / block_width), rolling_shutter_time, exposure_time};
     p.ids_sorted = gaussian_ids_sorted;
     p.tile_bins = reinterpret_cast<const int2 *>(tile_bins);
-    p.packed = reinterpret_cast<const PackedGaussian *>(packed_ws);
+    p.packed = reinterpret_cast<const PackedGaussian *>(packed);
     p.background = background;
     p.final_Ts = final_Ts; p.final_idx = final_idx; p.v_out = v_output; p.v_out_alpha = v_output_alpha;
     p.v_xy = v_xy; p.v_xy_abs = v_xy_abs; p.v_pix_vel = v_pix_vels; p.v_conic = v_conic; p.v_rgb = v_colors;
@@ -283,4 +275,38 @@ extern "C" int b200_rasterize_backward(int num_points, unsigned img_height, unsi
         case 9: return launch_bwd<9>(p, st);
         default: return launch_bwd<10>(p, st);
     }
+}
+
+extern "C" int b200_blend_backward_packed(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                                          unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                          const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
+                                          float exposure_time, const float *background, const float *final_Ts,
+                                          const int32_t *final_idx, const float *v_output, const float *v_output_alpha,
+                                          float *v_xy, float *v_xy_abs, float *v_pix_vels, float *v_conic,
+                                          float *v_colors, float *v_opacity, void *stream) {
+    return run_blend_backward(num_points, img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted,
+                              tile_bins, packed, rolling_shutter_time, exposure_time, background, final_Ts, final_idx,
+                              v_output, v_output_alpha, v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity,
+                              as_stream(stream));
+}
+
+extern "C" int b200_rasterize_backward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                                       unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                       const int32_t *tile_bins, const float *xys, const float *pix_vels,
+                                       float rolling_shutter_time, float exposure_time, const float *conics,
+                                       const float *colors, const float *opacities, const float *background,
+                                       const float *final_Ts, const int32_t *final_idx, const float *v_output,
+                                       const float *v_output_alpha, void *packed_ws, float *v_xy, float *v_xy_abs,
+                                       float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity,
+                                       void *stream) {
+    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
+    B200_REQUIRE(gaussian_ids_sorted && tile_bins && xys && pix_vels && conics && colors && opacities && background,
+                 "null input pointer");
+    B200_REQUIRE(packed_ws && aligned16(packed_ws), "packed_ws must be a 16-byte aligned scratch buffer");
+    cudaStream_t st = as_stream(stream);
+    int rc = launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed_ws, st);
+    if (rc) return rc;
+    return run_blend_backward(num_points, img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted,
+                              tile_bins, packed_ws, rolling_shutter_time, exposure_time, background, final_Ts, final_idx,
+                              v_output, v_output_alpha, v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity, st);
 }

@@ -140,6 +140,24 @@ __device__ __forceinline__ unsigned sample_mask(const PackedGaussian &g, const W
     return m;
 }
 
+// Tile-level version of sample_mask with a run-time sample count: can Gaussian `g` reach alpha >= 1/255 at any pixel
+// centre of the rectangle [x0,x1]x[y0,y1] for any of the S blur samples, given the rolling-shutter offsets [r0,r1] of
+// the rectangle's rows?  Conservative in the same way (padded extents, monotone float bounds, NaN => keep).
+__device__ __forceinline__ bool may_touch_rect(const PackedGaussian &g, float x0, float x1, float y0, float y1, float r0,
+                                               float r1, float exposure, int S) {
+    if (g.hx < 0.f) return false;
+    for (int s = 0; s < S; ++s) {
+        const float b = (S > 1) ? ((float)s / (float)(S - 1) - 0.5f) * exposure : 0.0f;
+        const float t0 = b + r0, t1 = b + r1;
+        const float ax = t0 * g.vx, bx = t1 * g.vx, ay = t0 * g.vy, by = t1 * g.vy;
+        const float cx0 = g.x + fminf(ax, bx), cx1 = g.x + fmaxf(ax, bx);
+        const float cy0 = g.y + fminf(ay, by), cy1 = g.y + fmaxf(ay, by);
+        const bool out = (cx0 - g.hx > x1) || (cx1 + g.hx < x0) || (cy0 - g.hy > y1) || (cy1 + g.hy < y0);
+        if (!out) return true;
+    }
+    return false;
+}
+
 #endif
 
 }  // namespace b200

@@ -163,31 +163,23 @@ using namespace b200;
 
 extern "C" size_t b200_packed_record_bytes(void) { return sizeof(PackedGaussian); }
 
-extern "C" int b200_rasterize_forward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
-                                      unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
-                                      const int32_t *tile_bins, const float *xys, const float *pix_vels,
-                                      float rolling_shutter_time, float exposure_time, const float *conics,
-                                      const float *colors, const float *opacities, const float *background,
-                                      void *packed_ws, float *out_img, float *final_Ts, int32_t *final_idx,
-                                      void *stream) {
+static int run_blend_forward(unsigned img_height, unsigned img_width, unsigned block_width, unsigned n_blur_samples,
+                             const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const void *packed,
+                             float rolling_shutter_time, float exposure_time, const float *background, float *out_img,
+                             float *final_Ts, int32_t *final_idx, cudaStream_t st) {
     B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");  // bindings.cu:450-452
-    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
     B200_REQUIRE(img_height > 0 && img_width > 0, "image size must be positive");
-    B200_REQUIRE(gaussian_ids_sorted && tile_bins && xys && pix_vels && conics && colors && opacities && background,
-                 "null input pointer");
-    B200_REQUIRE(packed_ws && aligned16(packed_ws), "packed_ws must be a 16-byte aligned scratch buffer");
+    B200_REQUIRE(tile_bins && background && packed, "null input pointer");
+    B200_REQUIRE(aligned16(packed), "packed records must be 16-byte aligned");
     B200_REQUIRE(out_img && final_Ts && final_idx, "null output pointer");
-    cudaStream_t st = as_stream(stream);
-    int rc = launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed_ws, st);
-    if (rc) return rc;
     BlendFwdParams p;
     p.g = BlendGeom{(int)img_height, (int)img_width, (int)block_width,
                     (int)((img_width + block_width - 1) / block_width),
                     (int)((img_height + block_width - 1) / block_width), rolling_shutter_time, exposure_time};
     p.ids_sorted = gaussian_ids_sorted;
     p.tile_bins = reinterpret_cast<const int2 *>(tile_bins);
-    p.packed = reinterpret_cast<const PackedGaussian *>(packed_ws);
+    p.packed = reinterpret_cast<const PackedGaussian *>(packed);
     p.background = background;
     p.out_img = out_img; p.final_Ts = final_Ts; p.final_idx = final_idx;
     switch (n_blur_samples) {
@@ -202,4 +194,41 @@ extern "C" int b200_rasterize_forward(int num_points, unsigned img_height, unsig
         case 9: return launch_fwd<9>(p, st);
         default: return launch_fwd<10>(p, st);
     }
+}
+
+extern "C" int b200_pack_records(int num_points, const float *xys, const float *pix_vels, const float *conics,
+                                 const float *colors, const float *opacities, void *packed, void *stream) {
+    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
+    B200_REQUIRE(xys && pix_vels && conics && colors && opacities, "null input pointer");
+    B200_REQUIRE(packed && aligned16(packed), "packed must be a 16-byte aligned buffer");
+    return launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed, as_stream(stream));
+}
+
+extern "C" int b200_blend_forward_packed(unsigned img_height, unsigned img_width, unsigned block_width,
+                                         unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                         const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
+                                         float exposure_time, const float *background, float *out_img, float *final_Ts,
+                                         int32_t *final_idx, void *stream) {
+    return run_blend_forward(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed,
+                             rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx,
+                             as_stream(stream));
+}
+
+extern "C" int b200_rasterize_forward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                                      unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                      const int32_t *tile_bins, const float *xys, const float *pix_vels,
+                                      float rolling_shutter_time, float exposure_time, const float *conics,
+                                      const float *colors, const float *opacities, const float *background,
+                                      void *packed_ws, float *out_img, float *final_Ts, int32_t *final_idx,
+                                      void *stream) {
+    B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");  // bindings.cu:450-452
+    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
+    B200_REQUIRE(gaussian_ids_sorted && tile_bins && xys && pix_vels && conics && colors && opacities && background,
+                 "null input pointer");
+    B200_REQUIRE(packed_ws && aligned16(packed_ws), "packed_ws must be a 16-byte aligned scratch buffer");
+    cudaStream_t st = as_stream(stream);
+    int rc = launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed_ws, st);
+    if (rc) return rc;
+    return run_blend_forward(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed_ws,
+                             rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx, st);
 }

@@ -35,6 +35,14 @@ SIGNATURES = {
     "b200_get_tile_bin_edges": (_i, [_i, _i, _p, _p, _p]),
     "b200_bin_tiles_ws_bytes": (_sz, [_i, _i]),
     "b200_bin_tiles": (_i, [_i, _i, _p, _p, _p, _p, _u, _u, _u, _p, _sz, _p, _p, _p]),
+    "b200_bin_cull_ws_bytes": (_sz, [_i]),
+    "b200_bin_cull_emit_ws_bytes": (_sz, [_i]),
+    "b200_bin_cull_count": (_i, [_i, _p, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _sz, _p, _p]),
+    "b200_bin_cull_emit": (_i, [_i, _i, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _p, _sz, _p, _p, _p]),
+    "b200_pack_records": (_i, [_i, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_blend_forward_packed": (_i, [_u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p]),
+    "b200_blend_backward_packed": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p,
+                                        _p, _p, _p, _p, _p, _p, _p]),
     "b200_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -99,7 +107,7 @@ def require_cuda(*tensors):
 # Set B200SPLAT_SYNC_CHECKS=1 to get the reference's immediate (synchronising) behaviour.
 SYNC_CHECKS = os.environ.get("B200SPLAT_SYNC_CHECKS", "0") == "1"
 _pending_flags = {}   # device index -> int32 device tensor awaiting a read-back
-_host_scratch = {}    # device index -> pinned int32[2] (total, flag)
+_host_scratch = {}    # device index -> pinned int32[8]: [0] total, [1] flag (scan path); [0:4] totals, [4] flag (cull path)
 
 
 def new_quat_flag(device):
@@ -115,6 +123,11 @@ def take_pending_flag(device):
 def host_scratch(device):
     buf = _host_scratch.get(device.index)
     if buf is None:
-        buf = torch.zeros(2, dtype=torch.int32).pin_memory()
+        buf = torch.zeros(8, dtype=torch.int32).pin_memory()
         _host_scratch[device.index] = buf
     return buf
+
+
+def raise_if_flagged(flag_value):
+    if int(flag_value) != 0:
+        raise AssertionError("quats must be normalized")  # deferred project_gaussians.py:69

@@ -205,8 +205,8 @@ def cumulative_intersects(num_tiles_hit):
                                              ptr(flag), stream()))
         torch.cuda.current_stream().synchronize()  # the one host sync of the path (utils.py:124 `.item()`)
         total = int(host[0])
-        if flag is not None and int(host[1]) != 0:
-            raise AssertionError("quats must be normalized")  # deferred project_gaussians.py:69
+        if flag is not None:
+            _lib.raise_if_flagged(host[1])
     return total, cum
 
 
@@ -227,6 +227,86 @@ def bin_tiles(num_intersects, xys, depths, radii, num_tiles_hit, tile_bounds, bl
                                  int(tile_bounds[0]), int(tile_bounds[1]), int(block_width), ptr(ws), nbytes, ptr(ids),
                                  ptr(bins), stream()))
     return ids, bins
+
+
+def pack_records(xys, pix_vels, conics, colors, opacities):
+    """Extension: the 64-byte per-Gaussian blend records (uint8 tensor of N * 64 bytes)."""
+    require_cuda(xys, pix_vels, conics, colors, opacities)
+    with torch.cuda.device(xys.device):
+        n = xys.size(0)
+        packed = _packed_ws(n, xys.device)
+        check(_lib.load().b200_pack_records(n, ptr(_f32(xys)), ptr(_f32(pix_vels)), ptr(_f32(conics)), ptr(_f32(colors)),
+                                            ptr(_f32(opacities)), ptr(packed), stream()))
+    return packed
+
+
+def bin_cull(packed, depths, radii, num_tiles_hit, img_height, img_width, block_width, n_blur_samples,
+             rolling_shutter_time, exposure_time):
+    """Extension: culled two-level binning -> (num_intersects_reference, gaussian_ids_sorted (M,), tile_bins (tiles,2)).
+    One host sync (the entry count M must be known to allocate), shared with the deferred quaternion check."""
+    require_cuda(packed, depths, radii, num_tiles_hit)
+    dev = depths.device
+    with torch.cuda.device(dev):
+        lib = _lib.load()
+        n = depths.numel()
+        H, W, bw, S = int(img_height), int(img_width), int(block_width), int(n_blur_samples)
+        rs, ex = float(rolling_shutter_time), float(exposure_time)
+        ws_bytes = lib.b200_bin_cull_ws_bytes(n)
+        ws_g = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        host = _lib.host_scratch(dev)
+        check(lib.b200_bin_cull_count(n, ptr(packed), ptr(_f32(depths)), ptr(radii), ptr(num_tiles_hit), H, W, bw, S, rs, ex,
+                                      ptr(ws_g), ws_bytes, host.data_ptr(), stream()))
+        flag = _lib.take_pending_flag(dev)
+        if flag is not None:
+            host[4:5].copy_(flag, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the one host sync of the path
+        if flag is not None:
+            _lib.raise_if_flagged(host[4])
+        total_ref, m = int(host[0]), int(host[3])
+        tiles = ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
+        ids = torch.empty((m,), dtype=torch.int32, device=dev)
+        bins = torch.empty((tiles, 2), dtype=torch.int32, device=dev)
+        e_bytes = lib.b200_bin_cull_emit_ws_bytes(m)
+        ws_e = torch.empty((e_bytes,), dtype=torch.uint8, device=dev)
+        check(lib.b200_bin_cull_emit(n, m, ptr(packed), ptr(radii), ptr(num_tiles_hit), H, W, bw, S, rs, ex, ptr(ws_g), ptr(ws_e),
+                                     e_bytes, ptr(ids), ptr(bins), stream()))
+    return total_ref, ids, bins
+
+
+def blend_forward_packed(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed,
+                         rolling_shutter_time, exposure_time, background):
+    """Extension: blend forward on prepacked records -> (out_img, final_Ts, final_idx)."""
+    require_cuda(gaussian_ids_sorted, tile_bins, packed, background)
+    dev = packed.device
+    H, W, S = int(img_height), int(img_width), int(n_blur_samples)
+    with torch.cuda.device(dev):
+        out_img = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+        final_Ts = torch.empty((H, W, S), dtype=torch.float32, device=dev)
+        final_idx = torch.empty((H, W, S), dtype=torch.int32, device=dev)
+        check(_lib.load().b200_blend_forward_packed(H, W, int(block_width), S, ptr(gaussian_ids_sorted), ptr(tile_bins),
+                                                    ptr(packed), float(rolling_shutter_time), float(exposure_time),
+                                                    ptr(_f32(background)), ptr(out_img), ptr(final_Ts), ptr(final_idx), stream()))
+    return out_img, final_Ts, final_idx
+
+
+def blend_backward_packed(num_points, img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins,
+                          packed, rolling_shutter_time, exposure_time, background, final_Ts, final_idx, v_output,
+                          v_output_alpha):
+    """Extension: blend backward on prepacked records -> (v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity)."""
+    require_cuda(gaussian_ids_sorted, tile_bins, packed, background)
+    dev = packed.device
+    with torch.cuda.device(dev):
+        n = int(num_points)
+        f32 = dict(dtype=torch.float32, device=dev)
+        v_output, v_output_alpha = _f32(v_output).contiguous(), _f32(v_output_alpha).contiguous()
+        v_xy, v_xy_abs, v_pix = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n, 2), **f32)
+        v_conic, v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
+        check(_lib.load().b200_blend_backward_packed(
+            n, int(img_height), int(img_width), int(block_width), int(n_blur_samples), ptr(gaussian_ids_sorted),
+            ptr(tile_bins), ptr(packed), float(rolling_shutter_time), float(exposure_time), ptr(_f32(background)),
+            ptr(_f32(final_Ts)), ptr(final_idx), ptr(v_output), ptr(v_output_alpha), ptr(v_xy), ptr(v_xy_abs), ptr(v_pix),
+            ptr(v_conic), ptr(v_colors), ptr(v_opacity), stream()))
+    return v_xy, v_xy_abs, v_pix, v_conic, v_colors, v_opacity
 
 
 def _geom(tile_bounds, block, img_size):

@@ -60,7 +60,21 @@ class _RasterizeGaussians(Function):
         block = (block_width, block_width, 1)
         img_size = (img_width, img_height, 1)
 
-        num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
+        three = colors.shape[-1] == 3
+        packed = None
+        if three:
+            # RGB path: pack once, culled two-level binning (ONE host sync: the culled entry count), blend.  The id
+            # lists hold only the (tile, Gaussian) pairs that can colour a pixel, in the reference's order; every
+            # output is identical to blending the reference's full lists (tests/test_gpu_parity.py).
+            n_samples = int(blur_samples)
+            if not (0 < n_samples <= 10):
+                raise RuntimeError("unsupported blur size")  # bindings.cu:450-452
+            packed = _C.pack_records(xys, pix_vels, conics, colors, opacity)
+            num_intersects, gaussian_ids_sorted, tile_bins = _C.bin_cull(
+                packed, depths, radii, num_tiles_hit, img_height, img_width, block_width, n_samples,
+                rolling_shutter_time, exposure_time)
+        else:
+            num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
 
         if num_intersects < 1:
             # reference behaviour for an empty render (rasterize.py:136-144): background image, final_Ts = 0
@@ -69,13 +83,14 @@ class _RasterizeGaussians(Function):
             tile_bins = torch.zeros(0, 2, device=xys.device)
             final_Ts = torch.zeros(img_height, img_width, blur_samples, device=xys.device)
             final_idx = torch.zeros(img_height, img_width, blur_samples, device=xys.device)
+        elif three:
+            out_img, final_Ts, final_idx = _C.blend_forward_packed(
+                img_height, img_width, block_width, blur_samples, gaussian_ids_sorted, tile_bins, packed,
+                rolling_shutter_time, exposure_time, background)
         else:
-            # only the per-tile id lists are consumed below, so the fused two-level binning is used; it yields the
-            # same gaussian_ids_sorted / tile_bins as bin_and_sort_gaussians(...)[3:5] (tests/test_gpu_parity.py)
             gaussian_ids_sorted, tile_bins = _C.bin_tiles(num_intersects, xys, depths, radii, num_tiles_hit,
                                                           tile_bounds, block_width)
-            rasterize_fn = _C.rasterize_forward if colors.shape[-1] == 3 else _C.nd_rasterize_forward
-            out_img, final_Ts, final_idx = rasterize_fn(
+            out_img, final_Ts, final_idx = _C.nd_rasterize_forward(
                 tile_bounds, block, img_size, blur_samples, gaussian_ids_sorted, tile_bins, xys, pix_vels,
                 rolling_shutter_time, exposure_time, conics, colors, opacity, background)
 
@@ -86,8 +101,9 @@ class _RasterizeGaussians(Function):
         ctx.blur_samples = blur_samples
         ctx.rolling_shutter_time = rolling_shutter_time
         ctx.exposure_time = exposure_time
+        ctx.has_packed = packed is not None
         ctx.save_for_backward(gaussian_ids_sorted, tile_bins, xys, pix_vels, conics, colors, opacity, background,
-                              final_Ts, final_idx)
+                              final_Ts, final_idx, packed if packed is not None else background)
         if return_alpha:
             final_T_mean = final_Ts.mean(dim=-1) if final_Ts.dim() == 3 else final_Ts
             return out_img, 1 - final_T_mean
@@ -98,7 +114,7 @@ class _RasterizeGaussians(Function):
         if v_out_alpha is None:
             v_out_alpha = torch.zeros_like(v_out_img[..., 0])
         (gaussian_ids_sorted, tile_bins, xys, pix_vels, conics, colors, opacity, background, final_Ts,
-         final_idx) = ctx.saved_tensors
+         final_idx, packed) = ctx.saved_tensors
 
         if ctx.num_intersects < 1:
             v_xy = torch.zeros_like(xys)
@@ -107,9 +123,14 @@ class _RasterizeGaussians(Function):
             v_conic = torch.zeros_like(conics)
             v_colors = torch.zeros_like(colors)
             v_opacity = torch.zeros_like(opacity)
+        elif ctx.has_packed:
+            v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity = _C.blend_backward_packed(
+                xys.size(0), ctx.img_height, ctx.img_width, ctx.block_width, ctx.blur_samples, gaussian_ids_sorted,
+                tile_bins, packed, ctx.rolling_shutter_time, ctx.exposure_time, background, final_Ts, final_idx,
+                v_out_img.contiguous(), v_out_alpha.contiguous())
+            v_opacity = v_opacity.reshape(opacity.shape)
         else:
-            rasterize_fn = _C.rasterize_backward if colors.shape[-1] == 3 else _C.nd_rasterize_backward
-            v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity = rasterize_fn(
+            v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity = _C.nd_rasterize_backward(
                 ctx.img_height, ctx.img_width, ctx.block_width, ctx.blur_samples, gaussian_ids_sorted, tile_bins,
                 xys, pix_vels, ctx.rolling_shutter_time, ctx.exposure_time, conics, colors, opacity, background,
                 final_Ts, final_idx, v_out_img.contiguous(), v_out_alpha.contiguous())

@@ -144,6 +144,47 @@ B200_API int b200_bin_tiles(int num_points, int num_intersects, const float *xys
                             unsigned block_width, void *ws, size_t ws_bytes, int32_t *gaussian_ids_sorted,
                             int32_t *tile_bins, void *stream);
 
+/* Culled binning -- the path gsplat.rasterize_gaussians takes.  Same two-level sort, but a (tile, Gaussian) pair of
+ * the reference's bbox (forward.cu:94-102: the square around a 3-sigma circle, inflated by the blur length) is kept only
+ * if the Gaussian can reach alpha >= 1/255 inside that tile for some blur sample; dropped pairs cannot change any pixel,
+ * survivors keep the reference's order, and the reference's phantom copies of Gaussian 0 survive iff it can touch
+ * tile 0.  Two calls around ONE host sync:
+ *   b200_bin_cull_count: per-Gaussian survivor counts, depth sort, offsets; totals_host_pinned[4] (HOST, pinned,
+ *       async) = {sum(num_tiles_hit) i.e. the reference's num_intersects, phantom slots, Gaussian-0-touches-tile-0,
+ *       culled entry count M};
+ *   b200_bin_cull_emit: after the caller synchronised and allocated M ids -> gaussian_ids_sorted (M), tile_bins.
+ * `packed` = records from b200_pack_records; ws_g (b200_bin_cull_ws_bytes(N) bytes) must stay alive and untouched
+ * between the two calls; ws_e has b200_bin_cull_emit_ws_bytes(M) bytes; both 256-byte aligned. */
+B200_API size_t b200_bin_cull_ws_bytes(int num_points);
+B200_API size_t b200_bin_cull_emit_ws_bytes(int num_entries);
+B200_API int b200_bin_cull_count(int num_points, const void *packed, const float *depths, const int32_t *radii,
+                                 const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
+                                 unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
+                                 float exposure_time, void *ws_g, size_t ws_g_bytes, int32_t *totals_host_pinned,
+                                 void *stream);
+B200_API int b200_bin_cull_emit(int num_points, int num_entries, const void *packed, const int32_t *radii,
+                                const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
+                                unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
+                                float exposure_time, const void *ws_g, void *ws_e, size_t ws_e_bytes,
+                                int32_t *gaussian_ids_sorted, int32_t *tile_bins, void *stream);
+
+/* Packed-record variants of the blend: b200_rasterize_forward/backward = b200_pack_records + these.  Lets a caller pack
+ * once per render and share the records between culled binning, forward and backward. */
+B200_API int b200_pack_records(int num_points, const float *xys, const float *pix_vels, const float *conics,
+                               const float *colors, const float *opacities, void *packed, void *stream);
+B200_API int b200_blend_forward_packed(unsigned img_height, unsigned img_width, unsigned block_width,
+                                       unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                       const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
+                                       float exposure_time, const float *background, float *out_img, float *final_Ts,
+                                       int32_t *final_idx, void *stream);
+B200_API int b200_blend_backward_packed(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
+                                        unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                        const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
+                                        float exposure_time, const float *background, const float *final_Ts,
+                                        const int32_t *final_idx, const float *v_output, const float *v_output_alpha,
+                                        float *v_xy, float *v_xy_abs, float *v_pix_vels, float *v_conic,
+                                        float *v_colors, float *v_opacity, void *stream);
+
 /* ---- blend (blur + rolling shutter), 3 channels ------------------------------------------
  * replaces rasterize_forward_tensor (bindings.h:110-127, bindings.cu:424-503; kernel forward.cu:306-456).
  * packed_ws: scratch of num_points * b200_packed_record_bytes() bytes, 16-byte aligned (filled here).

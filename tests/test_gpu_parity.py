@@ -255,6 +255,48 @@ def test_fused_two_level_binning_is_order_identical(name, n, motion, H, W, bw):
     assert np.array_equal(ids.cpu().numpy(), b["gaussian_ids_sorted"])
 
 
+@pytest.mark.parametrize("name,n,motion,S,rs,exposure,H,W", [
+    ("c2", None, True, 5, 0.0, 1 / 60, None, None), ("c2", 50000, True, 10, 1 / 50, 1 / 60, 256, 320),
+    ("c1", None, False, 1, 0.0, 0.0, None, None), ("c4", 80000, True, 5, 1 / 50, 1 / 60, 480, 640)])
+def test_culled_binning_changes_no_output(name, n, motion, S, rs, exposure, H, W):
+    """rasterize_gaussians bins with the culled two-level sort.  Dropped (tile, Gaussian) pairs can never colour a pixel,
+    so against a blend of the reference's FULL lists: image and transmittances are bit-identical, every last
+    contributor is the same Gaussian, each culled tile list is an order-preserving sub-list, gradients agree."""
+    d = scene_np(name, n=n, motion=motion, S=S, rs=rs, exposure=exposure, H=H, W=W)
+    o = oracle_project(d)
+    col = cu(oracle_colors(d))
+    opac = cu((d["opacity"][:, 0] * o["compensation"])[:, None].astype(np.float32))
+    xys, depths, pv, radii, conics, nth = (cu(o[k]) for k in ("xys", "depths", "pix_vels", "radii", "conics", "num_tiles_hit"))
+    bg = cu(d["background"])
+    tb = ((d["W"] + 15) // 16, (d["H"] + 15) // 16, 1)
+    m, cum = gsplat.compute_cumulative_intersects(nth)
+    ids_full, bins_full = gsplat.bin_and_sort_gaussians(d["N"], m, xys, depths, radii, cum, tb, 16)[3:5]
+    img_f, Ts_f, fi_f = _C.rasterize_forward(tb, (16, 16, 1), (d["W"], d["H"], 1), d["S"], ids_full, bins_full, xys, pv, d["rs"],
+                                             d["exposure"], conics, col, opac, bg)
+    packed = _C.pack_records(xys, pv, conics, col, opac)
+    total, ids_c, bins_c = _C.bin_cull(packed, depths, radii, nth, d["H"], d["W"], 16, d["S"], d["rs"], d["exposure"])
+    assert total == m and ids_c.numel() <= m
+    img_c, Ts_c, fi_c = _C.blend_forward_packed(d["H"], d["W"], 16, d["S"], ids_c, bins_c, packed, d["rs"], d["exposure"], bg)
+    assert torch.equal(img_c, img_f) and torch.equal(Ts_c, Ts_f)
+    hit = Ts_f < 1.0  # pixel-samples with at least one contributor
+    assert torch.equal(ids_c[fi_c[hit].long()], ids_full[fi_f[hit].long()])
+    # sub-list property on a sample of tiles
+    bf, bc, idf, idc = bins_full.cpu().numpy(), bins_c.cpu().numpy(), ids_full.cpu().numpy(), ids_c.cpu().numpy()
+    for t in np.random.default_rng(0).choice(bf.shape[0], size=min(40, bf.shape[0]), replace=False):
+        full, cul = idf[bf[t, 0]:bf[t, 1]], idc[bc[t, 0]:bc[t, 1]]
+        it = iter(full.tolist())
+        assert all(any(x == y for y in it) for x in cul.tolist()), f"tile {t}: culled list is not a sub-list"
+    g = np.random.default_rng(3)
+    v_out = cu(g.standard_normal((d["H"], d["W"], 3)).astype(np.float32))
+    v_alpha = cu(g.standard_normal((d["H"], d["W"])).astype(np.float32))
+    gf = _C.rasterize_backward(d["H"], d["W"], 16, d["S"], ids_full, bins_full, xys, pv, d["rs"], d["exposure"], conics, col, opac,
+                               bg, Ts_f, fi_f, v_out, v_alpha)
+    gc = _C.blend_backward_packed(d["N"], d["H"], d["W"], 16, d["S"], ids_c, bins_c, packed, d["rs"], d["exposure"], bg, Ts_c, fi_c,
+                                  v_out, v_alpha)
+    for a, b_, k in zip(gc, gf, ["v_xy", "v_xy_abs", "v_pix_vels", "v_conic", "v_colors", "v_opacity"]):
+        grad_close(a, b_.cpu().numpy(), 1e-5, k, rtol=1e-4, outliers=1e-5)  # only the atomic order differs
+
+
 def test_map_and_bins_golden_reference(golden):
     g = golden("map_bins.npz")
     H, W, bw = int(g["H"]), int(g["W"]), int(g["bw"])
