@@ -1,5 +1,6 @@
 // ABI version + thread-local error string of libb200splat.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -18,6 +19,15 @@ void set_error(const char *fmt, ...) {
 namespace b200 {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace b200
+namespace b200 {
+// Measured on B200 (tools/blend_probe.py, culled lists, config 2 / 3 / 4): two pixels per lane help the forward
+// (-5 % / -22 % / -26 %) but hurt the backward (+5 % / +17 % / +5 %: 111 registers -> 16 warps per SM), hence the defaults.
+int blend_pixels_per_lane(bool backward) {
+    static const int fwd = [] { const char *e = getenv("B200_BLEND_PPL_FWD"); return (e && e[0] == '1') ? 1 : 2; }();
+    static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '2') ? 2 : 1; }();
+    return backward ? bwd : fwd;
+}
 }  // namespace b200
 extern "C" long long b200_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
 extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }

@@ -60,57 +60,63 @@ __device__ __forceinline__ float butterfly16(const float (&v)[16], int lane) {
     return w1;
 }
 
-template <int S>
-__global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const BlendBwdParams p) {
+template <int S, int PPL>
+__global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_backward_kernel(const BlendBwdParams p) {
+    constexpr int NT = BLEND_THREADS / PPL;
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
-    __shared__ int s_max[BLEND_THREADS / 32];
+    __shared__ int s_max[NT / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int tile_x = tile % p.g.tbx, tile_y = tile / p.g.tbx;
-    int lx, ly;
-    bool has_pixel;
-    tile_pixel(p.g.bw, tid, lx, ly, has_pixel);
-    const int j = tile_x * p.g.bw + lx, i = tile_y * p.g.bw + ly;
-    const bool inside = has_pixel && i < p.g.H && j < p.g.W;
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const size_t pix = inside ? (size_t)i * p.g.W + j : 0;
-
-    const float roll = (float)((double)p.g.rs_time * ((double)(py / (float)p.g.H) - 0.5));
-    float tau[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-        tau[s] = ((S > 1) ? ((float)s / (float)(S - 1) - 0.5f) * p.g.exposure : 0.0f) + roll;
-
     const int2 range = p.tile_bins[tile];
     const float inv_s = 1.0f / (float)S;
+    const float bg0 = __ldg(p.background), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
 
+    bool inside[PPL];
+    float px[PPL], py[PPL], roll[PPL];
     // per-pixel cotangents and per-sample state (backward.cu:198-217)
-    float vo0 = 0.f, vo1 = 0.f, vo2 = 0.f, voa = 0.f;
-    if (inside) {
-        vo0 = p.v_out[3 * pix]; vo1 = p.v_out[3 * pix + 1]; vo2 = p.v_out[3 * pix + 2];
-        voa = p.v_out_alpha[pix];
-    }
-    const float bgdot = __ldg(p.background) * vo0 + __ldg(p.background + 1) * vo1 + __ldg(p.background + 2) * vo2;
-    float Tm[S], Kc[S], bdot[S];  // Tm = T / S
-    int bin_final[S];
+    float vo[PPL][3];
+    float Tm[PPL][S], Kc[PPL][S], bdot[PPL][S];  // Tm = T / S
+    int bin_final[PPL][S];
     int my_max = -1;
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        Tm[s] = inv_s; Kc[s] = 0.f; bdot[s] = 0.f; bin_final[s] = -1;
-        if (inside) {
-            const float Tf = p.final_Ts[pix * S + s];
-            Tm[s] = Tf * inv_s;
-            Kc[s] = Tf * inv_s * (voa - bgdot);
-            bin_final[s] = min(p.final_idx[pix * S + s], range.y - 1);  // batches only cover [range.x, range.y)
-            my_max = max(my_max, bin_final[s]);
+    for (int q = 0; q < PPL; ++q) {
+        int lx, ly;
+        bool has_pixel;
+        tile_pixel_ppl<PPL>(p.g.bw, tid, q, lx, ly, has_pixel);
+        const int j = tile_x * p.g.bw + lx, i = tile_y * p.g.bw + ly;
+        inside[q] = has_pixel && i < p.g.H && j < p.g.W;
+        px[q] = (float)j + 0.5f; py[q] = (float)i + 0.5f;
+        roll[q] = (float)((double)p.g.rs_time * ((double)(py[q] / (float)p.g.H) - 0.5));
+        const size_t pix = inside[q] ? (size_t)i * p.g.W + j : 0;
+        float voa = 0.f;
+        vo[q][0] = vo[q][1] = vo[q][2] = 0.f;
+        if (inside[q]) {
+            vo[q][0] = p.v_out[3 * pix]; vo[q][1] = p.v_out[3 * pix + 1]; vo[q][2] = p.v_out[3 * pix + 2];
+            voa = p.v_out_alpha[pix];
+        }
+        const float bgdot = bg0 * vo[q][0] + bg1 * vo[q][1] + bg2 * vo[q][2];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            Tm[q][s] = inv_s; Kc[q][s] = 0.f; bdot[q][s] = 0.f; bin_final[q][s] = -1;
+            if (inside[q]) {
+                const float Tf = p.final_Ts[pix * S + s];
+                Tm[q][s] = Tf * inv_s;
+                Kc[q][s] = Tf * inv_s * (voa - bgdot);
+                bin_final[q][s] = min(p.final_idx[pix * S + s], range.y - 1);  // batches only cover [range.x, range.y)
+                my_max = max(my_max, bin_final[q][s]);
+            }
         }
     }
+    float blur[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) blur[s] = blur_offset<S>(s, p.g.exposure);
+
     const int wmax = __reduce_max_sync(0xffffffffu, my_max);  // last contributor over the warp's pixel-samples
     if (lane == 0) s_max[warp] = wmax;
-
-    const WarpWindow win = warp_window(inside, px, py, roll);
+    const WarpWindow win = warp_window<PPL>(inside, px, py, roll);
 
     if (tid == 0) {
 #pragma unroll
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
     __syncthreads();
     int hi = -1;
 #pragma unroll
-    for (int w = 0; w < BLEND_THREADS / 32; ++w) hi = max(hi, s_max[w]);
+    for (int w = 0; w < NT / 32; ++w) hi = max(hi, s_max[w]);
     const int total = hi - range.x + 1;  // entries hi, hi-1, ..., range.x
     const int nb = total > 0 ? (total + BLEND_BATCH - 1) / BLEND_BATCH : 0;
 
@@ -145,9 +151,13 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
         const int top = hi - b * BLEND_BATCH;
         const int cnt = min(BLEND_BATCH, top - range.x + 1);
         if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], (uint32_t)cnt * (uint32_t)sizeof(PackedGaussian));
-        if (tid < cnt) {
-            const int g = __ldg(p.ids_sorted + top - tid);
-            tma_bulk_g2s(&s_rec[st][tid], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+#pragma unroll
+        for (int r = 0; r < PPL; ++r) {
+            const int e = tid + r * NT;
+            if (e < cnt) {
+                const int g = __ldg(p.ids_sorted + top - e);
+                tma_bulk_g2s(&s_rec[st][e], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+            }
         }
     };
 
@@ -175,40 +185,46 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
                     const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
                     const float cut = C.w + 1e-4f;
-                    const float cdot = C.x * vo0 + C.y * vo1 + C.z * vo2;
-                    float facsum = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, gxs = 0.f, gys = 0.f, gxa = 0.f, gya = 0.f,
-                          pvx = 0.f, pvy = 0.f, vop = 0.f;
+                    float vr = 0.f, vg = 0.f, vb = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, gxs = 0.f, gys = 0.f, gxa = 0.f,
+                          gya = 0.f, pvx = 0.f, pvy = 0.f, vop = 0.f;
                     bool any = false;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        if (!(smask & (1u << s)) || idx > bin_final[s]) continue;  // backward.cu:252-254 (bin_final = -1 outside)
-                        const float dx = A.x + tau[s] * A.z - px;
-                        const float dy = A.y + tau[s] * A.w - py;
-                        const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
-                        if (sigma > cut || sigma < 0.f) continue;
-                        const float vis = exp_neg_approx(sigma);
-                        const float ov = Bq.w * vis;
-                        const float alpha = fminf(0.99f, ov);
-                        if (alpha < 1.f / 255.f) continue;
-                        any = true;
-                        const float ra = rcp_approx(1.f - alpha);
-                        Tm[s] *= ra;  // T / S of backward.cu:294-296
-                        const float fac = alpha * Tm[s];
-                        const float v_alpha = Tm[s] * cdot + ra * (Kc[s] - bdot[s]);
-                        bdot[s] += fac * cdot;
-                        facsum += fac;
-                        const float v_sigma = -ov * v_alpha;  // no zeroing when the clamp is active (backward.cu:317)
-                        const float u = v_sigma * dx, w = v_sigma * dy;
-                        sxx += u * dx; sxy += u * dy; syy += w * dy;
-                        const float gx = Bq.x * u + Bq.y * w;
-                        const float gy = Bq.y * u + Bq.z * w;
-                        gxs += gx; gys += gy; gxa += fabsf(gx); gya += fabsf(gy);
-                        pvx += gx * tau[s]; pvy += gy * tau[s];
-                        vop += vis * v_alpha;
+                    for (int q = 0; q < PPL; ++q) {
+                        const float cdot = C.x * vo[q][0] + C.y * vo[q][1] + C.z * vo[q][2];
+                        float facsum = 0.f;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            if (!(smask & (1u << s)) || idx > bin_final[q][s]) continue;  // backward.cu:252-254
+                            const float tau = blur[s] + roll[q];
+                            const float dx = A.x + tau * A.z - px[q];
+                            const float dy = A.y + tau * A.w - py[q];
+                            const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
+                            if (sigma > cut || sigma < 0.f) continue;
+                            const float vis = exp_neg_approx(sigma);
+                            const float ov = Bq.w * vis;
+                            const float alpha = fminf(0.99f, ov);
+                            if (alpha < 1.f / 255.f) continue;
+                            any = true;
+                            const float ra = rcp_approx(1.f - alpha);
+                            Tm[q][s] *= ra;  // T / S of backward.cu:294-296
+                            const float fac = alpha * Tm[q][s];
+                            const float v_alpha = Tm[q][s] * cdot + ra * (Kc[q][s] - bdot[q][s]);
+                            bdot[q][s] += fac * cdot;
+                            facsum += fac;
+                            const float v_sigma = -ov * v_alpha;  // no zeroing when the clamp is active (backward.cu:317)
+                            const float u = v_sigma * dx, w = v_sigma * dy;
+                            sxx += u * dx; sxy += u * dy; syy += w * dy;
+                            const float gx = Bq.x * u + Bq.y * w;
+                            const float gy = Bq.y * u + Bq.z * w;
+                            gxs += gx; gys += gy; gxa += fabsf(gx); gya += fabsf(gy);
+                            pvx += gx * tau; pvy += gy * tau;
+                            vop += vis * v_alpha;
+                        }
+                        vr += facsum * vo[q][0]; vg += facsum * vo[q][1]; vb += facsum * vo[q][2];
                     }
                     if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
-                    const float v[16] = {facsum * vo0, facsum * vo1, facsum * vo2, 0.5f * sxx, sxy, 0.5f * syy,
-                                         gxs, gys, gxa, gya, pvx, pvy, vop, 0.f, 0.f, 0.f};
+                    const float v[16] = {vr, vg, vb, 0.5f * sxx, sxy, 0.5f * syy, gxs, gys, gxa, gya, pvx, pvy, vop,
+                                         0.f, 0.f, 0.f};
                     const float tot = butterfly16(v, lane);
                     if (my_dst && tot != 0.f) {
                         const int gid = s_rec[st][k].id;
@@ -223,7 +239,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(const Ble
 
 template <int S>
 static int launch_bwd(const BlendBwdParams &p, cudaStream_t st) {
-    blend_backward_kernel<S><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
+    if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2)
+        blend_backward_kernel<S, 2><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
+    else
+        blend_backward_kernel<S, 1><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -8,6 +8,10 @@ constexpr int BLEND_THREADS = 256;  // one CTA per tile; 8 warps, each owning an
 constexpr int BLEND_BATCH = 256;    // tile-list entries staged per pipeline stage
 constexpr int BLEND_STAGES = 2;
 
+// 1 or 2 pixels per lane in the blend kernels (B200_BLEND_PPL_FWD default 2, B200_BLEND_PPL_BWD default 1; only
+// 16x16 tiles can use 2)
+int blend_pixels_per_lane(bool backward);
+
 struct BlendGeom {
     int H, W, bw, tbx, tby;
     float rs_time, exposure;
@@ -88,6 +92,21 @@ __device__ __forceinline__ void tile_pixel(int bw, int tid, int &lx, int &ly, bo
     }
 }
 
+// PPL pixels per lane (register tiling).  PPL = 2 needs bw == 16: 4 warps per tile, warp w owns the 8x8 block
+// (w&1, w>>1) and lane l the pixels (l&7, (l>>3) + 4p), p = 0,1 -- half as many (warp, Gaussian) visits, so the
+// per-visit costs (cull, record loads, loop control, the backward's warp reduction + atomics) are paid half as often.
+template <int PPL>
+__device__ __forceinline__ void tile_pixel_ppl(int bw, int tid, int p, int &lx, int &ly, bool &has_pixel) {
+    if (PPL == 1) {
+        tile_pixel(bw, tid, lx, ly, has_pixel);
+    } else {
+        const int w = tid >> 5, lane = tid & 31;
+        lx = ((w & 1) << 3) + (lane & 7);
+        ly = ((w >> 1) << 3) + (lane >> 3) + 4 * p;
+        has_pixel = true;
+    }
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -105,12 +124,21 @@ struct WarpWindow {
     float x0, x1, y0, y1, r0, r1;
 };
 
-__device__ __forceinline__ WarpWindow warp_window(bool live, float px, float py, float roll) {
+template <int PPL>
+__device__ __forceinline__ WarpWindow warp_window(const bool (&live)[PPL], const float (&px)[PPL], const float (&py)[PPL],
+                                                  const float (&roll)[PPL]) {
     const float big = 3.0e38f;
+    float x0 = big, x1 = -big, y0 = big, y1 = -big, r0 = big, r1 = -big;
+#pragma unroll
+    for (int p = 0; p < PPL; ++p) {
+        if (live[p]) {
+            x0 = fminf(x0, px[p]); x1 = fmaxf(x1, px[p]); y0 = fminf(y0, py[p]); y1 = fmaxf(y1, py[p]);
+            r0 = fminf(r0, roll[p]); r1 = fmaxf(r1, roll[p]);
+        }
+    }
     WarpWindow w;
-    w.x0 = warp_min(live ? px : big); w.x1 = warp_max(live ? px : -big);
-    w.y0 = warp_min(live ? py : big); w.y1 = warp_max(live ? py : -big);
-    w.r0 = warp_min(live ? roll : big); w.r1 = warp_max(live ? roll : -big);
+    w.x0 = warp_min(x0); w.x1 = warp_max(x1); w.y0 = warp_min(y0); w.y1 = warp_max(y1);
+    w.r0 = warp_min(r0); w.r1 = warp_max(r1);
     return w;
 }
 

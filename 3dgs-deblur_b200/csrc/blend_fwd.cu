@@ -26,30 +26,33 @@ struct BlendFwdParams {
     int32_t *final_idx;       // (H,W,S)
 };
 
-template <int S>
-__global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const BlendFwdParams p) {
+template <int S, int PPL>
+__global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(const BlendFwdParams p) {
+    constexpr int NT = BLEND_THREADS / PPL;  // threads per tile
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x;
     const int tile_x = tile % p.g.tbx, tile_y = tile / p.g.tbx;
-    int lx, ly;
-    bool has_pixel;
-    tile_pixel(p.g.bw, tid, lx, ly, has_pixel);
-    const int j = tile_x * p.g.bw + lx, i = tile_y * p.g.bw + ly;
-    const bool inside = has_pixel && i < p.g.H && j < p.g.W;
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-
-    // per-sample time offsets: blur_rel of forward.cu:360-363
-    const float roll = (float)((double)p.g.rs_time * ((double)(py / (float)p.g.H) - 0.5));
-    float tau[S];
+    bool inside[PPL];
+    float px[PPL], py[PPL], roll[PPL];
+    int pi[PPL], pj[PPL];
 #pragma unroll
-    for (int s = 0; s < S; ++s)
-        tau[s] = ((S > 1) ? ((float)s / (float)(S - 1) - 0.5f) * p.g.exposure : 0.0f) + roll;
+    for (int q = 0; q < PPL; ++q) {
+        int lx, ly;
+        bool has_pixel;
+        tile_pixel_ppl<PPL>(p.g.bw, tid, q, lx, ly, has_pixel);
+        pj[q] = tile_x * p.g.bw + lx; pi[q] = tile_y * p.g.bw + ly;
+        inside[q] = has_pixel && pi[q] < p.g.H && pj[q] < p.g.W;
+        px[q] = (float)pj[q] + 0.5f; py[q] = (float)pi[q] + 0.5f;
+        roll[q] = (float)((double)p.g.rs_time * ((double)(py[q] / (float)p.g.H) - 0.5));  // forward.cu:360
+    }
+    float blur[S];  // blur_rel of forward.cu:363 without the roll part; tau = blur[s] + roll[q]
+#pragma unroll
+    for (int s = 0; s < S; ++s) blur[s] = blur_offset<S>(s, p.g.exposure);
 
-    // the warp's pixel rectangle and rolling-shutter window (live lanes only)
-    const WarpWindow win = warp_window(inside, px, py, roll);
+    const WarpWindow win = warp_window<PPL>(inside, px, py, roll);
 
     const int2 range = p.tile_bins[tile];
     const int total = range.y - range.x;
@@ -67,19 +70,34 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const Blen
         const int start = range.x + b * BLEND_BATCH;
         const int cnt = min(BLEND_BATCH, range.y - start);
         if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], (uint32_t)cnt * (uint32_t)sizeof(PackedGaussian));
-        if (tid < cnt) {
-            const int g = __ldg(p.ids_sorted + start + tid);
-            tma_bulk_g2s(&s_rec[st][tid], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+#pragma unroll
+        for (int r = 0; r < PPL; ++r) {
+            const int e = tid + r * NT;
+            if (e < cnt) {
+                const int g = __ldg(p.ids_sorted + start + e);
+                tma_bulk_g2s(&s_rec[st][e], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+            }
         }
     };
 
-    float T[S];
-    int last[S];
+    float T[PPL][S];
+    int last[PPL][S];
+    float acc[PPL][3];
+    unsigned alive[PPL];
 #pragma unroll
-    for (int s = 0; s < S; ++s) { T[s] = 1.f; last[s] = 0; }
-    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
-    unsigned alive = inside ? ((1u << S) - 1u) : 0u;
+    for (int q = 0; q < PPL; ++q) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) { T[q][s] = 1.f; last[q][s] = 0; }
+        acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+        alive[q] = inside[q] ? ((1u << S) - 1u) : 0u;
+    }
     const float inv_s = 1.0f / (float)S;
+    auto any_alive = [&]() {
+        unsigned a = 0u;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) a |= alive[q];
+        return a != 0u;
+    };
 
     int b = 0;
     bool pending = false;
@@ -92,7 +110,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const Blen
         const int start = range.x + b * BLEND_BATCH;
         const int cnt = min(BLEND_BATCH, range.y - start);
 
-        if (__any_sync(0xffffffffu, alive != 0u)) {
+        if (__any_sync(0xffffffffu, any_alive())) {
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int e = c0 + lane;
                 const unsigned my_mask = (e < cnt) ? sample_mask<S>(s_rec[st][e], win, p.g.exposure) : 0u;
@@ -101,58 +119,69 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(const Blen
                     const int src = __ffs(m) - 1;
                     const int k = c0 + src;
                     m &= m - 1;
-                    const unsigned live = alive & __shfl_sync(0xffffffffu, my_mask, src);
+                    const unsigned smask = __shfl_sync(0xffffffffu, my_mask, src);
                     const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
                     const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
                     const float cut = C.w + 1e-4f;
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        if (!(live & (1u << s))) continue;
-                        const float dx = A.x + tau[s] * A.z - px;
-                        const float dy = A.y + tau[s] * A.w - py;
-                        const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
-                        if (sigma > cut || sigma < 0.f) continue;  // alpha < 1/255 guaranteed above thr
-                        const float alpha = fminf(0.999f, Bq.w * exp_neg_approx(sigma));
-                        if (alpha < 1.f / 255.f) continue;
-                        const float next_T = T[s] * (1.f - alpha);
-                        if (next_T <= 1e-4f) {  // forward.cu:421-427: this sample is done, entry not blended
-                            alive &= ~(1u << s);
-                            continue;
+                        if (!(smask & (1u << s))) continue;  // warp-uniform
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            if (!(alive[q] & (1u << s))) continue;
+                            const float tau = blur[s] + roll[q];
+                            const float dx = A.x + tau * A.z - px[q];
+                            const float dy = A.y + tau * A.w - py[q];
+                            const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
+                            if (sigma > cut || sigma < 0.f) continue;  // alpha < 1/255 guaranteed above thr
+                            const float alpha = fminf(0.999f, Bq.w * exp_neg_approx(sigma));
+                            if (alpha < 1.f / 255.f) continue;
+                            const float next_T = T[q][s] * (1.f - alpha);
+                            if (next_T <= 1e-4f) {  // forward.cu:421-427: this sample is done, entry not blended
+                                alive[q] &= ~(1u << s);
+                                continue;
+                            }
+                            const float vis = alpha * T[q][s] * inv_s;
+                            acc[q][0] += C.x * vis; acc[q][1] += C.y * vis; acc[q][2] += C.z * vis;
+                            T[q][s] = next_T;
+                            last[q][s] = start + k;
                         }
-                        const float vis = alpha * T[s] * inv_s;
-                        acc_r += C.x * vis; acc_g += C.y * vis; acc_b += C.z * vis;
-                        T[s] = next_T;
-                        last[s] = start + k;
                     }
-                    if (!__any_sync(0xffffffffu, alive != 0u)) { m = 0; c0 = cnt; }
+                    if (!__any_sync(0xffffffffu, any_alive())) { m = 0; c0 = cnt; }
                 }
             }
         }
         // all warps are done with stage `st` (it is refilled two batches from now) + early exit vote
-        if (!__syncthreads_or(alive != 0u)) { ++b; break; }
+        if (!__syncthreads_or(any_alive())) { ++b; break; }
     }
     if (pending && b < nb) mbar_wait(&s_bar[b & 1], (uint32_t)((b >> 1) & 1));  // drain the prefetch before exit
 
-    if (inside) {
-        const size_t pix = (size_t)i * p.g.W + j;
+    const float bg0 = __ldg(p.background), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+        if (!inside[q]) continue;
+        const size_t pix = (size_t)pi[q] * p.g.W + pj[q];
         float meanT = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            meanT += T[s] * inv_s;
-            p.final_Ts[pix * S + s] = T[s];
-            p.final_idx[pix * S + s] = last[s];
+            meanT += T[q][s] * inv_s;
+            p.final_Ts[pix * S + s] = T[q][s];
+            p.final_idx[pix * S + s] = last[q][s];
         }
-        const float bg0 = __ldg(p.background), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
-        p.out_img[3 * pix] = acc_r + meanT * bg0;
-        p.out_img[3 * pix + 1] = acc_g + meanT * bg1;
-        p.out_img[3 * pix + 2] = acc_b + meanT * bg2;
+        p.out_img[3 * pix] = acc[q][0] + meanT * bg0;
+        p.out_img[3 * pix + 1] = acc[q][1] + meanT * bg1;
+        p.out_img[3 * pix + 2] = acc[q][2] + meanT * bg2;
     }
 }
 
 template <int S>
 static int launch_fwd(const BlendFwdParams &p, cudaStream_t st) {
-    blend_forward_kernel<S><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
+    // two pixels per lane when the tile is the full 16x16 (the only size Splatfacto uses, splatfacto.py:815)
+    if (p.g.bw == 16 && blend_pixels_per_lane(false) == 2)
+        blend_forward_kernel<S, 2><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
+    else
+        blend_forward_kernel<S, 1><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

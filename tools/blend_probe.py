@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--what", default="fwd,bwd")
+    ap.add_argument("--full", action="store_true", help="blend the reference's full tile lists instead of the culled ones")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     sc = synthetic.make_scene(a.config, device=dev, n_override=a.n)
@@ -40,13 +41,17 @@ def main():
     isect_s, gids_s = _C.sort_intersects(tb[0] * tb[1], isect, gids)
     bins = _C.get_tile_bin_edges(I, isect_s, tb)
     bg = sc["background"]
-    fwd = lambda: _C.rasterize_forward(tb, (16, 16, 1), (W, H, 1), S, gids_s, bins, xys, pix_vels, rs, ex, conics, colors, opac, bg)
+    packed = _C.pack_records(xys, pix_vels, conics, colors, opac)
+    if not a.full:
+        _, gids_s, bins = _C.bin_cull(packed, depths, radii, nth, H, W, 16, S, rs, ex)
+    fwd = lambda: _C.blend_forward_packed(H, W, 16, S, gids_s, bins, packed, rs, ex, bg)
     img, Ts, fi = fwd()
     v_out = torch.sign(img - cam["target"]) / img.numel()
     v_alpha = torch.zeros(H, W, device=dev)
-    bwd = lambda: _C.rasterize_backward(H, W, 16, S, gids_s, bins, xys, pix_vels, rs, ex, conics, colors, opac, bg, Ts, fi, v_out, v_alpha)
+    bwd = lambda: _C.blend_backward_packed(N, H, W, 16, S, gids_s, bins, packed, rs, ex, bg, Ts, fi, v_out, v_alpha)
     ln = (bins[:, 1] - bins[:, 0]).float()
-    print(f"config {a.config}: N={N} I={I} visible={int((nth > 0).sum())} tiles={bins.shape[0]} list len mean/max {ln.mean():.0f}/{ln.max():.0f}")
+    print(f"config {a.config}: N={N} I={I} list entries={gids_s.numel()} ({'full' if a.full else 'culled'}) visible={int((nth > 0).sum())} "
+          f"tiles={bins.shape[0]} list len mean/max {ln.mean():.0f}/{ln.max():.0f}")
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         if name not in a.what.split(","):
             continue
@@ -59,7 +64,7 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        print(f"{name}: {e0.elapsed_time(e1) / a.reps * 1000:.1f} us per call (pack + memsets + kernel)")
+        print(f"{name}: {e0.elapsed_time(e1) / a.reps * 1000:.1f} us per call (memsets + kernel)")
 
 
 if __name__ == "__main__":
