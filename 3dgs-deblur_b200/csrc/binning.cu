@@ -185,46 +185,137 @@ static BinTilesLayout bin_tiles_layout(int n, int m) {
 // reference's phantom copies of Gaussian 0 in tile 0 survive exactly when Gaussian 0 can touch tile 0.
 struct CullGeom {
     int H, W, bw, tbx, tby, S;
-    float rs_time, exposure;
+    float rs_time, exposure, inv_H, roll_eps;
 };
 
 __device__ __forceinline__ bool tile_survives(const PackedGaussian &g, int tx, int ty, const CullGeom &c) {
     const float x0 = (float)(tx * c.bw) + 0.5f, x1 = (float)min(c.W, (tx + 1) * c.bw) - 0.5f;
     const float y0 = (float)(ty * c.bw) + 0.5f, y1 = (float)min(c.H, (ty + 1) * c.bw) - 0.5f;
-    const float ra = (float)((double)c.rs_time * ((double)(y0 / (float)c.H) - 0.5));
-    const float rb = (float)((double)c.rs_time * ((double)(y1 / (float)c.H) - 0.5));
-    return may_touch_rect(g, x0, x1, y0, y1, fminf(ra, rb), fmaxf(ra, rb), c.exposure, c.S);
+    // rolling-shutter offsets of the tile's first / last row.  The blend computes them in double
+    // (forward.cu:360); here fp32 plus a margin of a few ulps of |rs_time| keeps the window conservative
+    // without touching the (vestigial on B200) fp64 pipe once per (tile, Gaussian) pair.
+    const float ra = c.rs_time * (y0 * c.inv_H - 0.5f), rb = c.rs_time * (y1 * c.inv_H - 0.5f);
+    return may_touch_rect(g, x0, x1, y0, y1, fminf(ra, rb) - c.roll_eps, fmaxf(ra, rb) + c.roll_eps, c.exposure, c.S);
 }
 
 // counters: [0] = sum of reserved slots (the reference's num_intersects), [1] = phantom slots,
-//           [2] = 1 if Gaussian 0 can touch tile 0, [3] = number of list entries after culling (filled later)
-__global__ void __launch_bounds__(256) cull_count_kernel(int n, const PackedGaussian *__restrict__ rec,
-                                                         const float *__restrict__ depths,
-                                                         const int32_t *__restrict__ radii,
-                                                         const int32_t *__restrict__ tiles_hit, CullGeom c,
-                                                         uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
-                                                         int32_t *__restrict__ survivors, int32_t *__restrict__ counters) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const int g = warp;
-    const int r = radii[g], reserved = tiles_hit[g];
-    int kept = 0, emitted_ref = 0;
-    if (r > 0 && reserved > 0) {
-        const PackedGaussian pg = rec[g];
-        int x0, y0, x1, y1;
-        tile_bbox(pg.x, pg.y, (float)r, c.tbx, c.tby, (float)c.bw, x0, y0, x1, y1);
-        const int w = x1 - x0;
-        emitted_ref = min(max(0, w * (y1 - y0)), reserved);
-        for (int k = lane; k < emitted_ref; k += 32) kept += tile_survives(pg, x0 + k % w, y0 + k / w, c) ? 1 : 0;
-        kept = __reduce_add_sync(0xffffffffu, kept);
-    }
-    if (lane == 0) {
-        survivors[g] = kept;
-        keys[g] = kept > 0 ? (uint32_t)__float_as_int(depths[g]) : 0xffffffffu;
+//           [2] = 1 if Gaussian 0 can touch tile 0, [3] = number of list entries after culling (filled later),
+//           [4] = number of 32-tile work chunks
+// Work is split into chunks of 32 candidate tiles (a screen-filling splat reserves 2500 of them, most reserve < 16):
+// one warp per chunk, chunk -> Gaussian by binary search in the chunk prefix sum, so a handful of huge splats
+// cannot serialise the pass.
+__global__ void __launch_bounds__(256) cull_prep_kernel(int n, const PackedGaussian *__restrict__ rec,
+                                                        const float *__restrict__ depths,
+                                                        const int32_t *__restrict__ radii,
+                                                        const int32_t *__restrict__ tiles_hit, CullGeom c,
+                                                        uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
+                                                        int4 *__restrict__ bbox, int32_t *__restrict__ chunks,
+                                                        int32_t *__restrict__ survivors, int32_t *__restrict__ cursor,
+                                                        int32_t *__restrict__ counters) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int reserved = 0, phantom = 0;
+    if (g < n) {
+        const int r = radii[g];
+        reserved = tiles_hit[g];
+        int x0 = 0, y0 = 0, w = 0, emitted_ref = 0;
+        if (r > 0 && reserved > 0) {
+            const float2 xy = *reinterpret_cast<const float2 *>(&rec[g].x);
+            int x1, y1;
+            tile_bbox(xy.x, xy.y, (float)r, c.tbx, c.tby, (float)c.bw, x0, y0, x1, y1);
+            w = x1 - x0;
+            emitted_ref = min(max(0, w * (y1 - y0)), reserved);
+        }
+        bbox[g] = make_int4(x0, y0, w, emitted_ref);
+        chunks[g] = (emitted_ref + 31) >> 5;
+        survivors[g] = 0;
+        cursor[g] = 0;
+        keys[g] = emitted_ref > 0 ? (uint32_t)__float_as_int(depths[g]) : 0xffffffffu;
         vals[g] = g;
-        if (reserved > 0) atomicAdd(counters + 0, reserved);
-        if (reserved - emitted_ref > 0) atomicAdd(counters + 1, reserved - emitted_ref);
+        phantom = max(0, reserved - emitted_ref);
         if (g == 0) counters[2] = tile_survives(rec[0], 0, 0, c) ? 1 : 0;
+    }
+    reserved = __reduce_add_sync(0xffffffffu, reserved);
+    phantom = __reduce_add_sync(0xffffffffu, phantom);
+    if ((threadIdx.x & 31) == 0) {
+        if (reserved) atomicAdd(counters + 0, reserved);
+        if (phantom) atomicAdd(counters + 1, phantom);
+    }
+}
+
+__global__ void cull_chunk_total_kernel(int n, const int32_t *__restrict__ chunk_off, const int32_t *__restrict__ chunks,
+                                        int32_t *__restrict__ counters) {
+    counters[4] = chunk_off[n - 1] + chunks[n - 1];
+}
+
+// largest g with chunk_off[g] <= chunk (chunk_off is the exclusive scan, non-decreasing)
+__device__ __forceinline__ int chunk_owner(const int32_t *__restrict__ chunk_off, int n, int chunk) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(chunk_off + mid) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) cull_chunks_kernel(int n, int total_entries,
+                                                          const PackedGaussian *__restrict__ rec,
+                                                          const int4 *__restrict__ bbox,
+                                                          const int32_t *__restrict__ chunk_off, CullGeom c,
+                                                          const int32_t *__restrict__ counters,
+                                                          int32_t *__restrict__ survivors,             // count pass
+                                                          const int32_t *__restrict__ pos_of,          // emit pass
+                                                          const int32_t *__restrict__ offs, int32_t *__restrict__ cursor,
+                                                          uint32_t *__restrict__ tile_keys, int32_t *__restrict__ ids) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int total_chunks = counters[4];
+    const int phantoms = counters[2] ? counters[1] : 0;
+    if (EMIT) {
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < min(phantoms, total_entries); k += gridDim.x * blockDim.x) {
+            tile_keys[k] = 0u;
+            ids[k] = 0;
+        }
+    }
+    for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < total_chunks; chunk += warps) {
+        const int g = chunk_owner(chunk_off, n, chunk);
+        const int4 bb = bbox[g];
+        const int k = ((chunk - __ldg(chunk_off + g)) << 5) + lane;
+        bool keep = false;
+        int tx = 0, ty = 0;
+        if (k < bb.w) {
+            tx = bb.x + k % bb.z; ty = bb.y + k / bb.z;
+            keep = tile_survives(rec[g], tx, ty, c);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0u) continue;
+        if (!EMIT) {
+            if (lane == 0) atomicAdd(survivors + g, __popc(m));
+        } else {
+            int base = 0;
+            if (lane == 0) base = phantoms + offs[pos_of[g]] + atomicAdd(cursor + g, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const int dst = base + __popc(m & ((1u << lane) - 1u));
+                if (dst < total_entries) {
+                    tile_keys[dst] = (uint32_t)(ty * c.tbx + tx);
+                    ids[dst] = g;
+                }
+            }
+        }
+    }
+}
+
+// survivors in depth order + the inverse permutation (Gaussian -> sorted position)
+__global__ void __launch_bounds__(256) gather_survivors_kernel(int n, const int32_t *__restrict__ order,
+                                                               const int32_t *__restrict__ survivors,
+                                                               int32_t *__restrict__ surv_sorted,
+                                                               int32_t *__restrict__ pos_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int g = order[i];
+        surv_sorted[i] = survivors[g];
+        pos_of[g] = i;
     }
 }
 
@@ -232,45 +323,6 @@ __global__ void cull_total_kernel(int n, const int32_t *__restrict__ offs, const
                                   int32_t *__restrict__ counters) {
     const int phantoms = counters[2] ? counters[1] : 0;
     counters[3] = phantoms + offs[n - 1] + surv_sorted[n - 1];
-}
-
-__global__ void __launch_bounds__(256) cull_emit_kernel(int n, int total, const int32_t *__restrict__ order,
-                                                        const int32_t *__restrict__ surv_sorted,
-                                                        const int32_t *__restrict__ offs,
-                                                        const PackedGaussian *__restrict__ rec,
-                                                        const int32_t *__restrict__ radii,
-                                                        const int32_t *__restrict__ tiles_hit, CullGeom c,
-                                                        const int32_t *__restrict__ counters,
-                                                        uint32_t *__restrict__ tile_keys, int32_t *__restrict__ ids) {
-    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
-    const int warp = gthread >> 5, lane = threadIdx.x & 31;
-    const int phantoms = counters[2] ? counters[1] : 0;
-    for (int k = gthread; k < min(phantoms, total); k += gridDim.x * blockDim.x) {
-        tile_keys[k] = 0u;
-        ids[k] = 0;
-    }
-    if (warp >= n) return;
-    if (surv_sorted[warp] <= 0) return;
-    const int g = order[warp];
-    const PackedGaussian pg = rec[g];
-    int x0, y0, x1, y1;
-    tile_bbox(pg.x, pg.y, (float)radii[g], c.tbx, c.tby, (float)c.bw, x0, y0, x1, y1);
-    const int w = x1 - x0;
-    const int emitted_ref = min(max(0, w * (y1 - y0)), tiles_hit[g]);
-    int base = phantoms + offs[warp];
-    for (int k0 = 0; k0 < emitted_ref; k0 += 32) {
-        const int k = k0 + lane;
-        const bool keep = k < emitted_ref && tile_survives(pg, x0 + k % w, y0 + k / w, c);
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int dst = base + __popc(m & ((1u << lane) - 1u));
-            if (dst < total) {
-                tile_keys[dst] = (uint32_t)((y0 + k / w) * c.tbx + (x0 + k % w));
-                ids[dst] = g;
-            }
-        }
-        base += __popc(m);
-    }
 }
 
 static int key_end_bit(int num_tiles) {
@@ -421,7 +473,8 @@ extern "C" int b200_bin_tiles(int num_points, int num_intersects, const float *x
 // Two workspaces: a per-Gaussian one (size known up front) that carries {order, survivors, offsets, counters} from
 // the count phase to the emit phase, and a per-entry one sized after the host has read the culled entry count.
 struct CullWsG {
-    size_t keys_a, keys_b, vals_a, order, survivors, surv_sorted, offs, counters, cub, cub_bytes, total;
+    size_t keys_a, keys_b, vals_a, order, survivors, surv_sorted, offs, bbox, chunks, chunk_off, cursor, pos_of, counters,
+        cub, cub_bytes, total;
 };
 static CullWsG cull_ws_g(int n) {
     CullWsG L;
@@ -429,7 +482,9 @@ static CullWsG cull_ws_g(int n) {
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
     L.keys_a = take(4 * (size_t)n); L.keys_b = take(4 * (size_t)n); L.vals_a = take(4 * (size_t)n);
     L.order = take(4 * (size_t)n); L.survivors = take(4 * (size_t)n); L.surv_sorted = take(4 * (size_t)n);
-    L.offs = take(4 * (size_t)n); L.counters = take(256);
+    L.offs = take(4 * (size_t)n); L.bbox = take(16 * (size_t)n); L.chunks = take(4 * (size_t)n);
+    L.chunk_off = take(4 * (size_t)n); L.cursor = take(4 * (size_t)n); L.pos_of = take(4 * (size_t)n);
+    L.counters = take(256);
     size_t b1 = 0, b3 = 0;
     cub::DeviceRadixSort::SortPairs((void *)nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32);
@@ -459,10 +514,14 @@ static CullWsE cull_ws_e(int m) {
 extern "C" size_t b200_bin_cull_ws_bytes(int num_points) { return cull_ws_g(num_points > 0 ? num_points : 1).total; }
 extern "C" size_t b200_bin_cull_emit_ws_bytes(int num_entries) { return cull_ws_e(num_entries > 0 ? num_entries : 1).total; }
 
+constexpr int CULL_GRID = 148 * 8;  // persistent warps, grid-stride over the chunk list
+
 static CullGeom make_cull_geom(unsigned H, unsigned W, unsigned bw, unsigned S, float rs, float exposure) {
     CullGeom c;
     c.H = (int)H; c.W = (int)W; c.bw = (int)bw; c.tbx = (int)((W + bw - 1) / bw); c.tby = (int)((H + bw - 1) / bw);
     c.S = (int)S; c.rs_time = rs; c.exposure = exposure;
+    c.inv_H = 1.0f / (float)H;
+    c.roll_eps = 4e-6f * fabsf(rs);
     return c;
 }
 
@@ -488,15 +547,24 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     size_t cub_bytes = L.cub_bytes;
     cudaStream_t st = as_stream(stream);
     const CullGeom c = make_cull_geom(img_height, img_width, block_width, n_blur_samples, rolling_shutter_time, exposure_time);
+    int4 *bbox = (int4 *)(base + L.bbox);
+    int32_t *chunks = (int32_t *)(base + L.chunks), *chunk_off = (int32_t *)(base + L.chunk_off);
+    int32_t *cursor = (int32_t *)(base + L.cursor), *pos_of = (int32_t *)(base + L.pos_of);
+    const PackedGaussian *rec = reinterpret_cast<const PackedGaussian *>(packed);
     B200_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-    const long long threads = 32ll * n;
-    cull_count_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(n, reinterpret_cast<const PackedGaussian *>(packed),
-                                                                    depths, radii, num_tiles_hit, c, keys_a, vals_a,
-                                                                    survivors, counters);
+    cull_prep_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, rec, depths, radii, num_tiles_hit, c, keys_a, vals_a, bbox, chunks,
+                                                       survivors, cursor, counters);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, chunks, chunk_off, n, st));
+    count_launch(2);
+    cull_chunk_total_kernel<<<1, 1, 0, st>>>(n, chunk_off, chunks, counters);
+    B200_LAUNCH_CHECK();
+    cull_chunks_kernel<false><<<CULL_GRID, 256, 0, st>>>(n, 0, rec, bbox, chunk_off, c, counters, survivors, nullptr, nullptr,
+                                                         nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
     B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, order, n, 0, 32, st));
     count_launch(5);
-    gather_counts_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, survivors, surv_sorted);
+    gather_survivors_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, survivors, surv_sorted, pos_of);
     B200_LAUNCH_CHECK();
     B200_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, surv_sorted, offs, n, st));
     count_launch(2);
@@ -526,17 +594,17 @@ extern "C" int b200_bin_cull_emit(int num_points, int num_entries, const void *p
     const CullWsE E = cull_ws_e(m);
     B200_REQUIRE(ws_e_bytes >= E.total, "workspace too small: %zu < %zu", ws_e_bytes, E.total);
     const char *gb = static_cast<const char *>(ws_g);
-    const int32_t *order = (const int32_t *)(gb + G.order), *surv_sorted = (const int32_t *)(gb + G.surv_sorted);
     const int32_t *offs = (const int32_t *)(gb + G.offs), *counters = (const int32_t *)(gb + G.counters);
+    const int4 *bbox = (const int4 *)(gb + G.bbox);
+    const int32_t *chunk_off = (const int32_t *)(gb + G.chunk_off), *pos_of = (const int32_t *)(gb + G.pos_of);
+    int32_t *cursor = (int32_t *)(const_cast<char *>(gb) + G.cursor);
     char *eb = static_cast<char *>(ws_e);
     uint32_t *tkeys_a = (uint32_t *)(eb + E.tkeys_a), *tkeys_b = (uint32_t *)(eb + E.tkeys_b);
     int32_t *ids_a = (int32_t *)(eb + E.ids_a);
     void *cub_ws = eb + E.cub;
     size_t cub_bytes = E.cub_bytes;
-    const long long threads = 32ll * n;
-    cull_emit_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(n, m, order, surv_sorted, offs,
-                                                                   reinterpret_cast<const PackedGaussian *>(packed), radii,
-                                                                   num_tiles_hit, c, counters, tkeys_a, ids_a);
+    cull_chunks_kernel<true><<<CULL_GRID, 256, 0, st>>>(n, m, reinterpret_cast<const PackedGaussian *>(packed), bbox, chunk_off,
+                                                        c, counters, nullptr, pos_of, offs, cursor, tkeys_a, ids_a);
     B200_LAUNCH_CHECK();
     int bits = key_end_bit(num_tiles) - 32;
     if (bits < 1) bits = 1;
