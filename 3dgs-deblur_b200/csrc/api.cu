@@ -21,11 +21,12 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace b200
 namespace b200 {
-// Measured on B200 (tools/blend_probe.py, culled lists, config 2 / 3 / 4): two pixels per lane help the forward
-// (-5 % / -22 % / -26 %) but hurt the backward (+5 % / +17 % / +5 %: 111 registers -> 16 warps per SM), hence the defaults.
+// Measured on B200 (tools/blend_probe.py, culled lists, config 2 / 3 / 4): two pixels per lane take the forward from
+// 472 / 2926 / 4527 us to 448 / 2285 / 3355 us and the backward (96 registers) from 864 / 4086 / 7641 us to
+// 841 / 4137 / 7207 us.  B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD = 1 select the one-pixel kernels.
 int blend_pixels_per_lane(bool backward) {
     static const int fwd = [] { const char *e = getenv("B200_BLEND_PPL_FWD"); return (e && e[0] == '1') ? 1 : 2; }();
-    static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '2') ? 2 : 1; }();
+    static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '1') ? 1 : 2; }();
     return backward ? bwd : fwd;
 }
 }  // namespace b200

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_backward_kernel(con
     float px[PPL], py[PPL], roll[PPL];
     // per-pixel cotangents and per-sample state (backward.cu:198-217)
     float vo[PPL][3];
-    float Tm[PPL][S], Kc[PPL][S], bdot[PPL][S];  // Tm = T / S
+    float Tm[PPL][S], D[PPL][S];  // Tm = T / S;  D = Tfinal/S * (v_alpha_out - bg.v_out) - sum_behind(fac * rgb.v_out)
     int bin_final[PPL][S];
     int my_max = -1;
 #pragma unroll
@@ -100,11 +100,11 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_backward_kernel(con
         const float bgdot = bg0 * vo[q][0] + bg1 * vo[q][1] + bg2 * vo[q][2];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            Tm[q][s] = inv_s; Kc[q][s] = 0.f; bdot[q][s] = 0.f; bin_final[q][s] = -1;
+            Tm[q][s] = inv_s; D[q][s] = 0.f; bin_final[q][s] = -1;
             if (inside[q]) {
                 const float Tf = p.final_Ts[pix * S + s];
                 Tm[q][s] = Tf * inv_s;
-                Kc[q][s] = Tf * inv_s * (voa - bgdot);
+                D[q][s] = Tf * inv_s * (voa - bgdot);
                 bin_final[q][s] = min(p.final_idx[pix * S + s], range.y - 1);  // batches only cover [range.x, range.y)
                 my_max = max(my_max, bin_final[q][s]);
             }
@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_backward_kernel(con
                             const float ra = rcp_approx(1.f - alpha);
                             Tm[q][s] *= ra;  // T / S of backward.cu:294-296
                             const float fac = alpha * Tm[q][s];
-                            const float v_alpha = Tm[q][s] * cdot + ra * (Kc[q][s] - bdot[q][s]);
-                            bdot[q][s] += fac * cdot;
+                            const float v_alpha = Tm[q][s] * cdot + ra * D[q][s];  // backward.cu:303-311
+                            D[q][s] -= fac * cdot;                                  // running buffer, :313-315
                             facsum += fac;
                             const float v_sigma = -ov * v_alpha;  // no zeroing when the clamp is active (backward.cu:317)
                             const float u = v_sigma * dx, w = v_sigma * dy;

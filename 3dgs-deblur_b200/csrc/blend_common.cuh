@@ -8,7 +8,7 @@ constexpr int BLEND_THREADS = 256;  // one CTA per tile; 8 warps, each owning an
 constexpr int BLEND_BATCH = 256;    // tile-list entries staged per pipeline stage
 constexpr int BLEND_STAGES = 2;
 
-// 1 or 2 pixels per lane in the blend kernels (B200_BLEND_PPL_FWD default 2, B200_BLEND_PPL_BWD default 1; only
+// 1 or 2 pixels per lane in the blend kernels (B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD, default 2; only
 // 16x16 tiles can use 2)
 int blend_pixels_per_lane(bool backward);
 

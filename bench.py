@@ -29,7 +29,7 @@ METRIC = "train images/sec (fwd+bwd) at N=5 blur samples"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "refgpu"])
     ap.add_argument("--config", default="c2")
