@@ -127,7 +127,7 @@ def run_cpu_arm(args, one_shot=False):
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arms
@@ -417,13 +417,36 @@ def run_gpu_arm(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(out), flush=True)
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner, ...) is
+    # sent to stderr instead, including C-level writes.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _run(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if _RESULT:
+        print(_RESULT[0], flush=True)
+
+
+_RESULT = []
+
+
+def _emit(obj):
+    _RESULT.append(json.dumps(obj))
+
+
+def _run(args):
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) == 0:
             run_cpu_arm(args)
