@@ -49,6 +49,11 @@ class FlatGaussians:
             p.grad = self.flat_grad[off:off + N * w].view(shapes[name])
             self.params[name] = p
             off += N * w
+        self.slices = {}
+        off2 = 0
+        for (name, _), w in zip(FIELDS, widths):
+            self.slices[name] = (off2, off2 + N * w)
+            off2 += N * w
         self.cam_vel: Optional[torch.Tensor] = None
         if extra:
             view = self.flat[off:off + extra].view(n_cameras, 6)
@@ -97,7 +102,7 @@ def render(model: FlatGaussians, cam: Dict, scene: Dict, cam_index: int = 0, sh_
 class ImageShardedTrainer:
     """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient allreduce per step."""
 
-    def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, comm_stream: bool = True):
+    def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True):
         self.model, self.scene = model, scene
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.group = group
@@ -106,6 +111,24 @@ class ImageShardedTrainer:
         fused = model.flat.is_cuda
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-15, fused=fused)
         self.step_idx = 0
+        # The SH coefficients are 48 of the 59 floats per Gaussian and their gradient is final as soon as the SH
+        # backward has run -- before the projection backward.  Their slice of the flat gradient buffer is reduced
+        # asynchronously from a post-accumulate hook, so most of the step's one exchange overlaps the rest of the
+        # backward pass; the remaining 11 floats per Gaussian (+ camera rows) follow when backward returns.
+        self._sh_work = None
+        self._sh_seen = 0
+        lo, hi = model.slices["sh_dc"][0], model.slices["sh_rest"][1]
+        self._sh_slice = model.flat_grad[lo:hi]
+        self._rest_slices = [model.flat_grad[:lo], model.flat_grad[hi:]]
+        self.overlap_sh = bool(overlap_sh and self.distributed)
+        if self.overlap_sh:
+            for name in ("sh_dc", "sh_rest"):
+                model.params[name].register_post_accumulate_grad_hook(self._on_sh_grad)
+
+    def _on_sh_grad(self, _param):
+        self._sh_seen += 1
+        if self._sh_seen == 2:  # both halves of the cat() have landed in the flat buffer
+            self._sh_work = dist.all_reduce(self._sh_slice, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def image_index(self, step: int, n_images: int) -> int:
         return (step * self.world + self.rank) % n_images
@@ -116,10 +139,17 @@ class ImageShardedTrainer:
         m.zero_grad()
         rgb, alpha, xys, radii = render(m, cam, self.scene, cam_index)
         loss = (rgb - target).abs().mean()
+        self._sh_seen, self._sh_work = 0, None
         loss.backward()
         if self.distributed:
             # gradients of the R images are averaged (each rank's loss is a per-image mean)
-            dist.all_reduce(m.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            if self._sh_work is not None:
+                for t in self._rest_slices:
+                    if t.numel():
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                self._sh_work.wait()
+            else:
+                dist.all_reduce(m.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             m.flat_grad.mul_(1.0 / self.world)
         self.opt.step()
         self.step_idx += 1
