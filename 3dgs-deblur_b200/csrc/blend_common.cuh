@@ -25,21 +25,13 @@ struct BlendGeom {
 //   (hx, hy) = half extents of the axis-aligned box around {sigma <= thr} (conservative, padded),
 //              +inf when the conic is not positive definite, -1 when nothing can pass (thr < 0).
 #ifdef __CUDACC__
-static __global__ void __launch_bounds__(256) pack_records_kernel(int n, const float2 *__restrict__ xys,
-                                                                  const float2 *__restrict__ pix_vels,
-                                                                  const float *__restrict__ conics,
-                                                                  const float *__restrict__ colors,
-                                                                  const float *__restrict__ opac,
-                                                                  PackedGaussian *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ PackedGaussian make_record(int id, float x, float y, float vx, float vy, float ca, float cb,
+                                                      float cc, float opac, float r, float g_, float b) {
     PackedGaussian g;
-    const float2 xy = xys[i], v = pix_vels[i];
-    g.x = xy.x; g.y = xy.y; g.vx = v.x; g.vy = v.y;
-    g.ca = conics[3 * (size_t)i]; g.cb = conics[3 * (size_t)i + 1]; g.cc = conics[3 * (size_t)i + 2];
-    g.opac = opac[i];
-    g.r = colors[3 * (size_t)i]; g.g = colors[3 * (size_t)i + 1]; g.b = colors[3 * (size_t)i + 2];
-    g.id = i;
+    g.x = x; g.y = y; g.vx = vx; g.vy = vy;
+    g.ca = ca; g.cb = cb; g.cc = cc; g.opac = opac;
+    g.r = r; g.g = g_; g.b = b;
+    g.id = id;
     g.pad = 0.f;
     const float thr = logf(255.f * g.opac);  // opac <= 0 -> -inf / NaN
     g.thr = thr;
@@ -54,11 +46,30 @@ static __global__ void __launch_bounds__(256) pack_records_kernel(int n, const f
     } else {
         g.hx = __int_as_float(0x7f800000); g.hy = __int_as_float(0x7f800000);  // unbounded: never culled
     }
-    float4 *o = reinterpret_cast<float4 *>(out + i);
+    return g;
+}
+
+__device__ __forceinline__ void store_record(PackedGaussian *dst, const PackedGaussian &g) {
+    float4 *o = reinterpret_cast<float4 *>(dst);
     o[0] = make_float4(g.x, g.y, g.vx, g.vy);
     o[1] = make_float4(g.ca, g.cb, g.cc, g.opac);
     o[2] = make_float4(g.r, g.g, g.b, g.thr);
     o[3] = make_float4(g.hx, g.hy, __int_as_float(g.id), 0.f);
+}
+
+static __global__ void __launch_bounds__(256) pack_records_kernel(int n, const float2 *__restrict__ xys,
+                                                                  const float2 *__restrict__ pix_vels,
+                                                                  const float *__restrict__ conics,
+                                                                  const float *__restrict__ colors,
+                                                                  const float *__restrict__ opac,
+                                                                  PackedGaussian *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 xy = xys[i], v = pix_vels[i];
+    const PackedGaussian g = make_record(i, xy.x, xy.y, v.x, v.y, conics[3 * (size_t)i], conics[3 * (size_t)i + 1],
+                                         conics[3 * (size_t)i + 2], opac[i], colors[3 * (size_t)i],
+                                         colors[3 * (size_t)i + 1], colors[3 * (size_t)i + 2]);
+    store_record(out + i, g);
 }
 
 static inline int launch_pack(int n, const float *xys, const float *pix_vels, const float *conics, const float *colors,

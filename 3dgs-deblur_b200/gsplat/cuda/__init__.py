@@ -69,7 +69,7 @@ def project_gaussians_forward(num_points, means3d, scales, glob_scale, quats, li
 def project_gaussians_backward(num_points, means3d, scales, glob_scale, quats, linear_velocity, angular_velocity,
                                rolling_shutter_time, exposure_time, viewmat, fx, fy, cx, cy, img_height, img_width,
                                cov3d, radii, conics, compensation, v_xy, v_depth, v_pix_vel, v_conic, v_compensation,
-                               _vel_tensors=None, _exact=False, _want_vel=False, _want_viewmat=False):
+                               _vel_tensors=None, _exact=False, _want_vel=False, _want_viewmat=False, _want_cov=True):
     """-> (v_cov2d, v_cov3d, v_mean3d, v_scale, v_quat)  [bindings.cu:259-358]
 
     The underscore keyword arguments are extensions used by gsplat.project_gaussians: with
@@ -83,8 +83,8 @@ def project_gaussians_backward(num_points, means3d, scales, glob_scale, quats, l
         f32 = dict(dtype=torch.float32, device=dev)
         v_xy, v_depth, v_pix_vel, v_conic, v_compensation = (
             _f32(t).contiguous() for t in (v_xy, v_depth, v_pix_vel, v_conic, v_compensation))
-        v_cov2d = torch.empty((n, 3), **f32)
-        v_cov3d = torch.empty((n, 6), **f32)
+        v_cov2d = torch.empty((n, 3), **f32) if _want_cov else None  # scratch outputs of the reference binding
+        v_cov3d = torch.empty((n, 6), **f32) if _want_cov else None
         v_mean3d = torch.empty((n, 3), **f32)
         v_scale = torch.empty((n, 3), **f32)
         v_quat = torch.empty((n, 4), **f32)

@@ -99,11 +99,35 @@ def render(model: FlatGaussians, cam: Dict, scene: Dict, cam_index: int = 0, sh_
     return rgb, alpha, xys, radii
 
 
+def render_fused(model: FlatGaussians, cam: Dict, scene: Dict, cam_index: int = 0, sh_degree_to_use: int = 3,
+                 write_grads_in_place: bool = True):
+    """Same render through gsplat.fused.render_gaussians (raw parameters in, one operator).  With
+    `write_grads_in_place` the backward kernel overwrites the model's flat gradient buffer directly."""
+    from gsplat.fused import render_gaussians
+
+    p = model.params
+    if model.cam_vel is not None:
+        vel = model.cam_vel[cam_index] + cam["vel0"]
+        lin, ang = vel[:3], vel[3:]
+    else:
+        lin, ang = cam["lin_vel"], cam["ang_vel"]
+    sink = {k: v.grad for k, v in p.items()} if write_grads_in_place else None
+    blur = scene["blur_samples"] if scene["exposure_time"] > 0 else 1
+    rgb, alpha, info = render_gaussians(
+        p["means"], p["log_scales"], p["quats"], p["opacity_logit"], p["sh_dc"], p["sh_rest"], cam["viewmat"],
+        cam["cam_pos"], lin, ang, cam["fx"], cam["fy"], cam["cx"], cam["cy"], scene["H"], scene["W"],
+        scene["block_width"], scene["background"], rolling_shutter_time=scene["rolling_shutter_time"],
+        exposure_time=scene["exposure_time"], blur_samples=blur, sh_degree_to_use=sh_degree_to_use, grad_sink=sink)
+    return rgb, alpha, info
+
+
 class ImageShardedTrainer:
     """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient allreduce per step."""
 
-    def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True):
+    def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True,
+                 fused: bool = False):
         self.model, self.scene = model, scene
+        self.fused = fused  # render through gsplat.fused (caller-modified path) instead of the three drop-in operators
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.group = group
         self.rank = dist.get_rank(group) if self.distributed else 0
@@ -120,7 +144,7 @@ class ImageShardedTrainer:
         lo, hi = model.slices["sh_dc"][0], model.slices["sh_rest"][1]
         self._sh_slice = model.flat_grad[lo:hi]
         self._rest_slices = [model.flat_grad[:lo], model.flat_grad[hi:]]
-        self.overlap_sh = bool(overlap_sh and self.distributed)
+        self.overlap_sh = bool(overlap_sh and self.distributed and not fused)  # fused: grads land in one kernel
         if self.overlap_sh:
             for name in ("sh_dc", "sh_rest"):
                 model.params[name].register_post_accumulate_grad_hook(self._on_sh_grad)
@@ -136,8 +160,14 @@ class ImageShardedTrainer:
     def train_step(self, cam: Dict, target: torch.Tensor, cam_index: int = 0):
         """fwd + L1 loss + bwd (+ allreduce) + Adam.  Returns the (device) loss tensor; no host sync."""
         m = self.model
-        m.zero_grad()
-        rgb, alpha, xys, radii = render(m, cam, self.scene, cam_index)
+        if self.fused:
+            if m.cam_vel is not None:
+                m.cam_vel.grad.zero_()  # the Gaussian rows are overwritten by the fused backward kernel
+            rgb, alpha, info = render_fused(m, cam, self.scene, cam_index)
+            xys, radii = None, info["radii"]
+        else:
+            m.zero_grad()
+            rgb, alpha, xys, radii = render(m, cam, self.scene, cam_index)
         loss = (rgb - target).abs().mean()
         self._sh_seen, self._sh_work = 0, None
         loss.backward()

@@ -97,7 +97,7 @@ class _ProjectGaussians(Function):
         out = _C.project_gaussians_backward(
             num_points, means3d, scales, glob_scale, quats, None, None, rs_time, exposure, viewmat, fx, fy, cx, cy,
             H, W, cov3d, radii, conics, compensation, v_xys, v_depths, v_pix_vels, v_conics, v_compensation,
-            _vel_tensors=(lin, ang), _exact=ctx.vel_grad, _want_vel=want_vel, _want_viewmat=want_vm)
+            _vel_tensors=(lin, ang), _exact=ctx.vel_grad, _want_vel=want_vel, _want_viewmat=want_vm, _want_cov=False)
         v_mean3d, v_scale, v_quat = out[2], out[3], out[4]
         rest = list(out[5:])
         v_lin = v_ang = v_viewmat = None

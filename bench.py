@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--no-vel-grad", action="store_true", help="camera velocities constant (reference CUDA-path mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--images", type=int, default=8, help="distinct training images per rank")
+    ap.add_argument("--fused", action="store_true",
+                    help="render through gsplat.fused.render_gaussians (caller-modified 'next' path) instead of the drop-in operators")
     return ap.parse_args()
 
 
@@ -205,7 +207,7 @@ def run_gpu_arm(args):
     targets = [t.to(dev).float() / 255 for t in targets_u8]
     vel_grad = not args.no_vel_grad
     model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
-    trainer = ImageShardedTrainer(model, scene_dev, lr=1e-4)
+    trainer = ImageShardedTrainer(model, scene_dev, lr=1e-4, fused=args.fused)
     H, W, S, N = scene["H"], scene["W"], scene["blur_samples"], scene["N"]
 
     def barrier():
@@ -412,7 +414,9 @@ def run_gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, S={S} blur samples, exposure 1/60 s (synthetic cozyroom stand-in, SURVEY 8d + free space)",
                    "step": "project+SH+bin/sort+blend fwd, L1, full bwd, grad allreduce (N>1), fused Adam; 1 image per GPU per step",
-                   "velocity_grad": vel_grad, "global_batch": world, "parallelism": f"image-sharded dp{world}",
+                   "velocity_grad": vel_grad, "global_batch": world,
+                   "api": ("gsplat.fused.render_gaussians (raw parameters, caller-modified)" if args.fused else
+                           "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians"), "parallelism": f"image-sharded dp{world}",
                    "l2": "per-step working set (59 floats x N x {param,grad,2 Adam moments} = %d MB) exceeds the 126 MB L2; no explicit flush" % (59 * N * 16 // 2**20)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,

@@ -206,6 +206,38 @@ B200_API int b200_rasterize_backward(int num_points, unsigned img_height, unsign
                             const float *v_output_alpha, void *packed_ws, float *v_xy, float *v_xy_abs,
                             float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity, void *stream);
 
+/* ---- fused pre/post-processing on RAW Splatfacto parameters ("next" row f-1 of SURVEY.md section 8) -----------------
+ * Folds the caller-side glue of nerfstudio/models/splatfacto.py:816-856 into one kernel each way:
+ *   forward : exp(log_scales), quats/|quats|, projection (b200_project_gaussians_forward semantics), "fast" SH colour
+ *             + clamp(rgb + 0.5, 0) for Gaussians that survive the bbox test, sigmoid(opacity_logit) * compensation,
+ *             and the packed blend record  ->  packed (N * b200_packed_record_bytes()), depths, radii, num_tiles_hit
+ *             (exactly the inputs of b200_bin_cull_count / b200_blend_*_packed).
+ *   backward: blend gradients (v_xy, v_pix_vel (N,2); v_conic, v_colors (N,3); v_opacity (N)) -> gradients of the raw
+ *             parameters, every row written (zeros for culled Gaussians), plus optional camera gradients
+ *             (g_lin_vel[3], g_ang_vel[3], g_viewmat[12]; overwritten).  Projection gradients are the clamp-aware
+ *             "exact" ones (B200_PROJ_EXACT).
+ * sh_dc (N,3) and sh_rest (N,K-1,3) are the two Splatfacto tensors (no torch.cat needed); sh_bases = K. */
+B200_API int b200_fused_preprocess_forward(int num_points, const float *means, const float *log_scales,
+                                           const float *quats, const float *opacity_logit, const float *sh_dc,
+                                           const float *sh_rest, int sh_bases, int degrees_to_use, const float *viewmat,
+                                           const float *cam_pos, const float *lin_vel, const float *ang_vel,
+                                           float rolling_shutter_time, float exposure_time, float fx, float fy, float cx,
+                                           float cy, unsigned img_height, unsigned img_width, unsigned block_width,
+                                           float clip_thresh, void *packed, float *depths, int32_t *radii,
+                                           int32_t *num_tiles_hit, void *stream);
+B200_API int b200_fused_preprocess_backward(int num_points, const float *means, const float *log_scales,
+                                            const float *quats, const float *opacity_logit, const float *sh_dc,
+                                            const float *sh_rest, int sh_bases, int degrees_to_use, const float *viewmat,
+                                            const float *cam_pos, const float *lin_vel, const float *ang_vel,
+                                            float rolling_shutter_time, float exposure_time, float fx, float fy, float cx,
+                                            float cy, unsigned img_height, unsigned img_width, unsigned block_width,
+                                            float clip_thresh, const void *packed, const int32_t *radii,
+                                            const float *v_xy, const float *v_pix_vel, const float *v_conic,
+                                            const float *v_colors, const float *v_opacity, float *g_means,
+                                            float *g_log_scales, float *g_quats, float *g_opacity_logit, float *g_sh_dc,
+                                            float *g_sh_rest, float *g_lin_vel, float *g_ang_vel, float *g_viewmat,
+                                            void *stream);
+
 /* ---- N-channel blend (no blur), fp16 accumulators like the reference ----------------------
  * replaces nd_rasterize_forward_tensor / nd_rasterize_backward_tensor (bindings.h:129-166,
  * bindings.cu:506-682; kernels forward.cu:185-304, backward.cu:22-141). */

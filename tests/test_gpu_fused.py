@@ -1,0 +1,125 @@
+"""GPU: gsplat.fused.render_gaussians (raw parameters, one operator) against the chain of drop-in
+operators Splatfacto uses (project_gaussians -> spherical_harmonics -> rasterize_gaussians), forward and backward."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from util_scene import cu, scene_np
+
+
+def _raw_scene(name, n, H, W, S, rs, ex, seed=0):
+    import gsplat.synthetic as synthetic
+
+    sc = synthetic.make_scene(name, device="cuda", n_override=n)
+    cam = sc["cameras"][0]
+    sc.update(H=H, W=W, blur_samples=S, rolling_shutter_time=rs, exposure_time=ex)
+    cam.update(fx=W / 2.0, fy=W / 2.0, cx=W / 2.0, cy=H / 2.0)
+    return sc, cam
+
+
+def _leaves(sc, cam):
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_dc", "sh_rest")
+    lv = {k: sc[k].clone().requires_grad_(True) for k in names}
+    lv["lin"] = cam["lin_vel"].clone().requires_grad_(True)
+    lv["ang"] = cam["ang_vel"].clone().requires_grad_(True)
+    lv["viewmat"] = cam["viewmat"].clone().requires_grad_(True)
+    lv["bg"] = sc["background"].clone().requires_grad_(True)
+    return lv
+
+
+def _chain(sc, cam, lv):
+    from gsplat import project_gaussians, rasterize_gaussians, spherical_harmonics
+
+    H, W = sc["H"], sc["W"]
+    q = lv["quats"] / lv["quats"].norm(dim=-1, keepdim=True)
+    xys, depths, pv, radii, conics, comp, nth, _ = project_gaussians(
+        lv["means"], torch.exp(lv["log_scales"]), 1, q, lv["lin"], lv["ang"], sc["rolling_shutter_time"], sc["exposure_time"],
+        lv["viewmat"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, 16)
+    colors = torch.cat((lv["sh_dc"], lv["sh_rest"]), dim=1)
+    rgbs = torch.clamp(spherical_harmonics(3, lv["means"].detach() - cam["cam_pos"], colors) + 0.5, min=0.0)
+    opac = torch.sigmoid(lv["opacity_logit"]) * comp[:, None]
+    S = sc["blur_samples"] if sc["exposure_time"] > 0 else 1
+    return rasterize_gaussians(xys, depths, pv, radii, conics, nth, rgbs, opac, H, W, 16, background=lv["bg"],
+                               return_alpha=True, rolling_shutter_time=sc["rolling_shutter_time"],
+                               exposure_time=sc["exposure_time"], blur_samples=S)
+
+
+def _fused(sc, cam, lv, sink=None):
+    from gsplat.fused import render_gaussians
+
+    S = sc["blur_samples"] if sc["exposure_time"] > 0 else 1
+    return render_gaussians(lv["means"], lv["log_scales"], lv["quats"], lv["opacity_logit"], lv["sh_dc"], lv["sh_rest"],
+                            lv["viewmat"], cam["cam_pos"], lv["lin"], lv["ang"], cam["fx"], cam["fy"], cam["cx"], cam["cy"],
+                            sc["H"], sc["W"], 16, lv["bg"], rolling_shutter_time=sc["rolling_shutter_time"],
+                            exposure_time=sc["exposure_time"], blur_samples=S, sh_degree_to_use=3, grad_sink=sink)
+
+
+def _rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name,n,H,W,S,rs,ex", [("c2", 40000, 256, 320, 5, 0.0, 1 / 60), ("c2", 40000, 192, 256, 3, 1 / 50, 1 / 60),
+                                                ("c1", 10000, 256, 256, 1, 0.0, 0.0)])
+def test_fused_render_matches_operator_chain(name, n, H, W, S, rs, ex):
+    sc, cam = _raw_scene(name, n, H, W, S, rs, ex)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    v_rgb = torch.randn(H, W, 3, device="cuda", generator=g)
+    v_a = torch.randn(H, W, device="cuda", generator=g)
+    a = _leaves(sc, cam)
+    rgb_a, alpha_a = _chain(sc, cam, a)
+    ((rgb_a * v_rgb).sum() + (alpha_a * v_a).sum()).backward()
+    b = _leaves(sc, cam)
+    rgb_b, alpha_b, info = _fused(sc, cam, b)
+    ((rgb_b * v_rgb).sum() + (alpha_b * v_a).sum()).backward()
+    # forward: same kernels, same lists; only sigmoid (fast exp) and the order of the SH dot product differ
+    # (a 1-ulp change of an opacity can flip one alpha >= 1/255 test: <= 1e-3 of the pixels may move by up to 1e-2)
+    for x, y in ((rgb_a, rgb_b), (alpha_a, alpha_b)):
+        diff = (x - y).abs()
+        assert float((diff > 2e-5).float().mean()) <= 1e-3 and float(diff.max()) < 1e-2
+    for k in ("means", "log_scales", "quats", "opacity_logit", "sh_dc", "sh_rest", "lin", "ang", "viewmat", "bg"):
+        assert a[k].grad is not None and b[k].grad is not None, k
+        assert _rel(b[k].grad, a[k].grad) < 3e-3, (k, _rel(b[k].grad, a[k].grad))
+    assert info["absgrad"].shape == (n, 2) and info["radii"].shape == (n,)
+
+
+def test_fused_grad_sink_writes_in_place_and_zeroes_culled_rows():
+    sc, cam = _raw_scene("c2", 20000, 128, 160, 5, 0.0, 1 / 60)
+    a = _leaves(sc, cam)
+    rgb, alpha, _ = _fused(sc, cam, a)
+    rgb.mean().backward()
+    b = _leaves(sc, cam)
+    sink = {k: torch.full_like(b[k], float("nan")) for k in ("means", "log_scales", "quats", "opacity_logit", "sh_dc", "sh_rest")}
+    rgb2, alpha2, info = _fused(sc, cam, b, sink=sink)
+    rgb2.mean().backward()
+    for k, t in sink.items():
+        assert torch.isfinite(t).all(), k  # every row overwritten, no NaN sentinel left
+        assert b[k].grad is None  # autograd returned nothing for sunk inputs
+        assert _rel(t, a[k].grad) < 1e-4, k
+    culled = info["radii"] == 0
+    assert culled.any() and (sink["sh_rest"][culled] == 0).all() and (sink["means"][culled] == 0).all()
+
+
+def test_fused_trainer_matches_unfused_trainer():
+    """Three optimizer steps through gsplat.dp with and without the fused path end at the same parameters."""
+    import gsplat.synthetic as synthetic
+    from gsplat.dp import FlatGaussians, ImageShardedTrainer
+
+    outs = []
+    for fused in (False, True):
+        sc = synthetic.make_scene("c2", device="cuda", n_override=20000, n_cameras=2)
+        sc.update(H=128, W=160)
+        cams = []
+        for c in sc["cameras"]:
+            c.update(fx=80.0, fy=80.0, cx=80.0, cy=64.0, vel0=torch.cat([c["lin_vel"], c["ang_vel"]]))
+            c["target"] = c["target"][:128, :160].contiguous()
+            cams.append(c)
+        model = FlatGaussians(sc, "cuda", n_cameras=2, optimize_velocities=True)
+        tr = ImageShardedTrainer(model, sc, lr=1e-3, fused=fused)
+        for k in range(3):
+            tr.train_step(cams[k % 2], cams[k % 2]["target"], k % 2)
+        outs.append(model.flat.detach().clone())
+    moved = (outs[0] - outs[1]).abs().max()
+    assert float(moved) < 5e-4, float(moved)  # Adam normalises, so tiny gradient differences stay tiny steps
