@@ -5,8 +5,6 @@ Same names, argument order and return tuples as the reference pybind module
 code and tests that do `import gsplat.cuda as _C` keep working.  Tensors are allocated here by
 PyTorch and handed to the C ABI (include/b200splat.h) as raw device pointers on the current stream.
 """
-import math
-
 import torch
 
 from .. import _lib

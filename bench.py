@@ -227,7 +227,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from gsplat import _lib, synthetic
-    from gsplat.dp import FlatGaussians, ImageShardedTrainer, render
+    from gsplat.dp import FlatGaussians, ImageShardedTrainer
 
     lib = _lib.load()
     n_img = args.images

@@ -1,6 +1,5 @@
 """`bench.py --impl refgpu`: the train step of bench.py on the UNMODIFIED reference CUDA kernels (oracle/_ref),
 same scene, same loss, same fused Adam, 1 GPU.  BENCH INFRASTRUCTURE ONLY (see ref_ops.py)."""
-import json
 import os
 import sys
 

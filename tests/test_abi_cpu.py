@@ -1,6 +1,5 @@
 """CPU: the C-ABI library loads, exports every symbol include/b200splat.h declares, the ctypes table
 matches the header, and argument errors are reported without touching a GPU."""
-import ctypes
 import os
 import re
 

@@ -1,12 +1,10 @@
 """GPU: gsplat.fused.render_gaussians (raw parameters, one operator) against the chain of drop-in
 operators Splatfacto uses (project_gaussians -> spherical_harmonics -> rasterize_gaussians), forward and backward."""
-import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-from util_scene import cu, scene_np
 
 
 def _raw_scene(name, n, H, W, S, rs, ex, seed=0):

@@ -5,14 +5,13 @@
 import argparse
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "3dgs-deblur_b200"))
 import torch
 
 import gsplat.cuda as _C
-from gsplat import _lib, synthetic
+from gsplat import synthetic
 
 
 def main():
