@@ -247,12 +247,18 @@ __global__ void cull_chunk_total_kernel(int n, const int32_t *__restrict__ chunk
     counters[4] = chunk_off[n - 1] + chunks[n - 1];
 }
 
-// largest g with chunk_off[g] <= chunk (chunk_off is the exclusive scan, non-decreasing)
-__device__ __forceinline__ int chunk_owner(const int32_t *__restrict__ chunk_off, int n, int chunk) {
-    int lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(chunk_off + mid) <= chunk) lo = mid; else hi = mid - 1;
+// largest g with chunk_off[g] <= chunk (chunk_off is the exclusive scan, non-decreasing).  Warp-cooperative 32-ary
+// search: every lane probes a different position, so 300k Gaussians take 4 dependent loads instead of 19.
+__device__ __forceinline__ int chunk_owner(const int32_t *__restrict__ chunk_off, int n, int chunk, int lane) {
+    int lo = 0, hi = n;  // invariant: chunk_off[lo] <= chunk, answer in [lo, hi)
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int idx = lo + (lane + 1) * step;
+        const bool ok = idx < hi && __ldg(chunk_off + idx) <= chunk;
+        const int k = __popc(__ballot_sync(0xffffffffu, ok));  // monotone predicate: lanes 0..k-1 are true
+        const int nlo = lo + k * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
     }
     return lo;
 }
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(256) cull_chunks_kernel(int n, int total_entri
         }
     }
     for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < total_chunks; chunk += warps) {
-        const int g = chunk_owner(chunk_off, n, chunk);
+        const int g = chunk_owner(chunk_off, n, chunk, lane);
         const int4 bb = bbox[g];
         const int k = ((chunk - __ldg(chunk_off + g)) << 5) + lane;
         bool keep = false;

@@ -139,6 +139,9 @@ class ImageShardedTrainer:
         # backward has run -- before the projection backward.  Their slice of the flat gradient buffer is reduced
         # asynchronously from a post-accumulate hook, so most of the step's one exchange overlaps the rest of the
         # backward pass; the remaining 11 floats per Gaussian (+ camera rows) follow when backward returns.
+        # NCCL averages in the collective itself; gloo (CPU tests) only sums, so the 1/R scale is a separate pass there
+        self._avg = self.distributed and dist.get_backend(group) == "nccl"
+        self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self._sh_work = None
         self._sh_seen = 0
         lo, hi = model.slices["sh_dc"][0], model.slices["sh_rest"][1]
@@ -152,7 +155,7 @@ class ImageShardedTrainer:
     def _on_sh_grad(self, _param):
         self._sh_seen += 1
         if self._sh_seen == 2:  # both halves of the cat() have landed in the flat buffer
-            self._sh_work = dist.all_reduce(self._sh_slice, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._sh_work = dist.all_reduce(self._sh_slice, op=self._op, group=self.group, async_op=True)
 
     def image_index(self, step: int, n_images: int) -> int:
         return (step * self.world + self.rank) % n_images
@@ -176,11 +179,12 @@ class ImageShardedTrainer:
             if self._sh_work is not None:
                 for t in self._rest_slices:
                     if t.numel():
-                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                        dist.all_reduce(t, op=self._op, group=self.group)
                 self._sh_work.wait()
             else:
-                dist.all_reduce(m.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-            m.flat_grad.mul_(1.0 / self.world)
+                dist.all_reduce(m.flat_grad, op=self._op, group=self.group)
+            if not self._avg:
+                m.flat_grad.mul_(1.0 / self.world)
         self.opt.step()
         self.step_idx += 1
         self.last_xys, self.last_radii = xys, radii
