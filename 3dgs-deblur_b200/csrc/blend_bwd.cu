@@ -61,7 +61,7 @@ __device__ __forceinline__ float butterfly16(const float (&v)[16], int lane) {
 }
 
 template <int S, int PPL>
-__global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_backward_kernel(const BlendBwdParams p) {
+__global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : 3) blend_backward_kernel(const BlendBwdParams p) {
     constexpr int NT = BLEND_THREADS / PPL;
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
@@ -185,42 +185,68 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_backward_kernel(con
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
                     const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
                     const float cut = C.w + 1e-4f;
-                    float vr = 0.f, vg = 0.f, vb = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, gxs = 0.f, gys = 0.f, gxa = 0.f,
-                          gya = 0.f, pvx = 0.f, pvy = 0.f, vop = 0.f;
-                    bool any = false;
+                    float sxx = 0.f, sxy = 0.f, syy = 0.f, gxs = 0.f, gys = 0.f, gxa = 0.f, gya = 0.f, pvx = 0.f, pvy = 0.f,
+                          vop = 0.f;
+                    float cdot[PPL], facsum[PPL];
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
-                        const float cdot = C.x * vo[q][0] + C.y * vo[q][1] + C.z * vo[q][2];
-                        float facsum = 0.f;
+                        cdot[q] = C.x * vo[q][0] + C.y * vo[q][1] + C.z * vo[q][2];
+                        facsum[q] = 0.f;
+                    }
+                    bool any = false;
 #pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            if (!(smask & (1u << s)) || idx > bin_final[q][s]) continue;  // backward.cu:252-254
-                            const float tau = blur[s] + roll[q];
-                            const float dx = A.x + tau * A.z - px[q];
-                            const float dy = A.y + tau * A.w - py[q];
-                            const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
-                            if (sigma > cut || sigma < 0.f) continue;
-                            const float vis = exp_neg_approx(sigma);
-                            const float ov = Bq.w * vis;
-                            const float alpha = fminf(0.99f, ov);
-                            if (alpha < 1.f / 255.f) continue;
-                            any = true;
-                            const float ra = rcp_approx(1.f - alpha);
-                            Tm[q][s] *= ra;  // T / S of backward.cu:294-296
-                            const float fac = alpha * Tm[q][s];
-                            const float v_alpha = Tm[q][s] * cdot + ra * D[q][s];  // backward.cu:303-311
-                            D[q][s] -= fac * cdot;                                  // running buffer, :313-315
-                            facsum += fac;
-                            const float v_sigma = -ov * v_alpha;  // no zeroing when the clamp is active (backward.cu:317)
-                            const float u = v_sigma * dx, w = v_sigma * dy;
-                            sxx += u * dx; sxy += u * dy; syy += w * dy;
+                    for (int s = 0; s < S; ++s) {
+                        if (!(smask & (1u << s))) continue;  // warp-uniform
+                        // The lane's PPL pixels are evaluated side by side in straight-line code (independent
+                        // dependency chains for the scheduler to interleave); invalid pixels are masked, not branched.
+                        float dx[PPL], dy[PPL], sigma[PPL], tau[PPL];
+                        bool ok[PPL], some = false;
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            tau[q] = blur[s] + roll[q];
+                            dx[q] = A.x + tau[q] * A.z - px[q];
+                            dy[q] = A.y + tau[q] * A.w - py[q];
+                            sigma[q] = 0.5f * (Bq.x * dx[q] * dx[q] + Bq.z * dy[q] * dy[q]) + Bq.y * dx[q] * dy[q];
+                            ok[q] = (idx <= bin_final[q][s]) && !(sigma[q] > cut || sigma[q] < 0.f);  // backward.cu:252-254,276
+                            some |= ok[q];
+                        }
+                        if (!some) continue;
+                        float vis[PPL], ov[PPL], alpha[PPL];
+                        some = false;
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            vis[q] = exp_neg_approx(ok[q] ? sigma[q] : 0.f);
+                            ov[q] = Bq.w * vis[q];
+                            alpha[q] = fminf(0.99f, ov[q]);
+                            ok[q] = ok[q] && !(alpha[q] < 1.f / 255.f);
+                            some |= ok[q];
+                        }
+                        if (!some) continue;
+                        any = true;
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            const float ra = rcp_approx(1.f - alpha[q]);
+                            const float Tn = Tm[q][s] * ra;  // T / S of backward.cu:294-296
+                            const float fac = alpha[q] * Tn;
+                            const float v_alpha = Tn * cdot[q] + ra * D[q][s];  // backward.cu:303-311
+                            // no zeroing when the clamp is active (backward.cu:317); masked pixels contribute exactly 0
+                            const float v_sigma = ok[q] ? -ov[q] * v_alpha : 0.f;
+                            Tm[q][s] = ok[q] ? Tn : Tm[q][s];
+                            D[q][s] = ok[q] ? D[q][s] - fac * cdot[q] : D[q][s];  // running buffer, :313-315
+                            facsum[q] += ok[q] ? fac : 0.f;
+                            const float u = v_sigma * dx[q], w = v_sigma * dy[q];
+                            sxx += u * dx[q]; sxy += u * dy[q]; syy += w * dy[q];
                             const float gx = Bq.x * u + Bq.y * w;
                             const float gy = Bq.y * u + Bq.z * w;
                             gxs += gx; gys += gy; gxa += fabsf(gx); gya += fabsf(gy);
-                            pvx += gx * tau; pvy += gy * tau;
-                            vop += vis * v_alpha;
+                            pvx += gx * tau[q]; pvy += gy * tau[q];
+                            vop += ok[q] ? vis[q] * v_alpha : 0.f;
                         }
-                        vr += facsum * vo[q][0]; vg += facsum * vo[q][1]; vb += facsum * vo[q][2];
+                    }
+                    float vr = 0.f, vg = 0.f, vb = 0.f;
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        vr += facsum[q] * vo[q][0]; vg += facsum[q] * vo[q][1]; vb += facsum[q] * vo[q][2];
                     }
                     if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
                     const float v[16] = {vr, vg, vb, 0.5f * sxx, sxy, 0.5f * syy, gxs, gys, gxa, gya, pvx, pvy, vop,
