@@ -22,8 +22,9 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace b200
 namespace b200 {
 // Measured on B200 (tools/blend_probe.py, culled lists, config 2 / 3 / 4): two pixels per lane take the forward from
-// 472 / 2926 / 4527 us to 448 / 2285 / 3355 us and the backward (96 registers) from 864 / 4086 / 7641 us to
-// 841 / 4137 / 7207 us.  B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD = 1 select the one-pixel kernels.
+// 472 / 2926 / 4527 us to 448 / 2285 / 3355 us and the backward from 864 / 4086 / 7641 us to 779 / 3414 / 6440 us
+// (pixels evaluated side by side with masked updates, 96 registers, 5 CTAs per SM).
+// B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD = 1 select the one-pixel kernels.
 int blend_pixels_per_lane(bool backward) {
     static const int fwd = [] { const char *e = getenv("B200_BLEND_PPL_FWD"); return (e && e[0] == '1') ? 1 : 2; }();
     static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '1') ? 1 : 2; }();

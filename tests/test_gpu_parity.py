@@ -588,3 +588,33 @@ def test_nd_rasterize_vs_oracle():
         _C.nd_rasterize_forward(tb, (16, 16, 1), (d["W"], d["H"], 1), 2, cu(b["gaussian_ids_sorted"]), cu(b["tile_bins"]),
                                 cu(r["proj"]["xys"]), cu(r["proj"]["pix_vels"]), 0.0, 0.1, cu(r["proj"]["conics"]),
                                 cu(cols), cu(r["opac"]), cu(bgc))
+
+
+def test_public_rasterize_nd_channels_and_uint8_colors():
+    """rasterize_gaussians with C != 3 (N-channel kernels, fp16 accumulators) and with uint8 colours (rasterize.py:63-65)."""
+    d = scene_np("c1", n=4000, H=64, W=80)
+    r = oracle_render(d)
+    g = np.random.default_rng(4)
+    xys, depths, pv, radii, conics, nth = (cu(r["proj"][k]) for k in ("xys", "depths", "pix_vels", "radii", "conics", "num_tiles_hit"))
+    opac = cu(r["opac"])
+    cols5 = g.uniform(0, 1, (d["N"], 5)).astype(np.float32)
+    bg5 = g.uniform(0, 1, 5).astype(np.float32)
+    c5 = cu(cols5).requires_grad_(True)
+    img5, alpha5 = rasterize_gaussians(xys, depths, pv, radii, conics, nth, c5, opac, d["H"], d["W"], 16, background=cu(bg5), return_alpha=True)
+    b = r["bins"]
+    ref = O.nd_rasterize_forward(d["H"], d["W"], 16, b["gaussian_ids_sorted"], b["tile_bins"], r["proj"]["xys"], r["proj"]["conics"], cols5,
+                                 r["opac"], bg5)
+    close(img5, ref[0], 2e-2, 1e-2, "5-channel image (fp16 accumulators)")
+    close(alpha5, 1 - ref[1], 1e-5, 1e-5, "5-channel alpha", outliers=1e-3, outlier_atol=1e-2)
+    img5.sum().backward()
+    assert c5.grad is not None and torch.isfinite(c5.grad).all() and float(c5.grad.abs().sum()) > 0
+    # uint8 colours are scaled to [0, 1] like the reference
+    u8 = (g.uniform(0, 1, (d["N"], 3)) * 255).astype(np.uint8)
+    img_u8 = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(u8), opac, d["H"], d["W"], 16, background=cu(d["background"]))
+    img_f = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(u8.astype(np.float32) / 255), opac, d["H"], d["W"], 16,
+                                background=cu(d["background"]))
+    assert torch.equal(img_u8, img_f)
+    # default background is ones (rasterize.py:71-74)
+    img_def = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(r["colors"]), opac, d["H"], d["W"], 16)
+    img_one = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(r["colors"]), opac, d["H"], d["W"], 16, background=torch.ones(3, device="cuda"))
+    assert torch.equal(img_def, img_one)
