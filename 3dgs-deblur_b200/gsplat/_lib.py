@@ -61,7 +61,9 @@ _LIB = None
 def load():
     """dlopen the library once and attach prototypes.  Raises if it has not been built."""
     global _LIB
-    if _LIB is None:
+    if _LIB is not None:
+        return _LIB
+    if True:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"libb200splat.so not found at {LIB_PATH}. Build it with "
@@ -90,6 +92,25 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+class on_device:
+    """`with on_device(dev):` = torch.cuda.device(dev) when dev is not already current, else a no-op (the common
+    single-GPU-per-process case: saves two cudaSetDevice round trips per operator call)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 def require_cuda(*tensors):

@@ -8,7 +8,7 @@ PyTorch and handed to the C ABI (include/b200splat.h) as raw device pointers on 
 import torch
 
 from .. import _lib
-from .._lib import check, ptr, require_cuda, stream
+from .._lib import check, on_device, ptr, require_cuda, stream
 
 __all__ = [
     "nd_rasterize_forward", "nd_rasterize_backward", "rasterize_forward", "rasterize_backward",
@@ -42,7 +42,7 @@ def project_gaussians_forward(num_points, means3d, scales, glob_scale, quats, li
     """-> (cov3d, xys, depths, pix_vels, radii, conics, compensation, num_tiles_hit)  [bindings.cu:154-257]"""
     require_cuda(means3d, scales, quats, viewmat)
     dev = means3d.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         lin, ang = _vel_tensors if _vel_tensors is not None else (_vel_tensor(linear_velocity, dev),
                                                                  _vel_tensor(angular_velocity, dev))
         n = int(num_points)
@@ -74,7 +74,7 @@ def project_gaussians_backward(num_points, means3d, scales, glob_scale, quats, l
     `_want_vel` / `_want_viewmat` the tuple grows by (v_lin_vel, v_ang_vel) / (v_viewmat (3,4))."""
     require_cuda(means3d, scales, quats, viewmat, cov3d, radii, conics, compensation)
     dev = means3d.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         lin, ang = _vel_tensors if _vel_tensors is not None else (_vel_tensor(linear_velocity, dev),
                                                                  _vel_tensor(angular_velocity, dev))
         n = int(num_points)
@@ -124,7 +124,7 @@ def compute_sh_forward(method, num_points, degree, degrees_to_use, viewdirs, coe
         raise RuntimeError("coeffs must have dimensions (N, D, 3)")
     viewdirs, coeffs = viewdirs.contiguous(), coeffs.contiguous()
     require_cuda(viewdirs, coeffs)
-    with torch.cuda.device(coeffs.device):
+    with on_device(coeffs.device):
         colors = torch.empty((n, 3), dtype=torch.float32, device=coeffs.device)
         check(_lib.load().b200_compute_sh_forward(_METHOD[method], n, int(degree), int(degrees_to_use),
                                                   ptr(_f32(viewdirs)), ptr(_f32(coeffs)), ptr(colors), stream()))
@@ -142,7 +142,7 @@ def compute_sh_backward(method, num_points, degree, degrees_to_use, viewdirs, v_
         raise RuntimeError("v_colors must have dimensions (N, 3)")
     viewdirs, v_colors = viewdirs.contiguous(), v_colors.contiguous()
     require_cuda(viewdirs, v_colors)
-    with torch.cuda.device(v_colors.device):
+    with on_device(v_colors.device):
         v_coeffs = torch.empty((n, num_sh_bases(degree), 3), dtype=torch.float32, device=v_colors.device)
         check(_lib.load().b200_compute_sh_backward(_METHOD[method], n, int(degree), int(degrees_to_use),
                                                    ptr(_f32(viewdirs)), ptr(_f32(v_colors)), ptr(v_coeffs), stream()))
@@ -152,7 +152,7 @@ def compute_sh_backward(method, num_points, degree, degrees_to_use, viewdirs, v_
 def map_gaussian_to_intersects(num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width):
     """-> (isect_ids (I,) i64, gaussian_ids (I,) i32)  [bindings.cu:360-402]"""
     require_cuda(xys, depths, radii, cum_tiles_hit)
-    with torch.cuda.device(xys.device):
+    with on_device(xys.device):
         m = int(num_intersects)
         isect = torch.empty((m,), dtype=torch.int64, device=xys.device)
         gids = torch.empty((m,), dtype=torch.int32, device=xys.device)
@@ -165,7 +165,7 @@ def map_gaussian_to_intersects(num_points, num_intersects, xys, depths, radii, c
 def sort_intersects(num_tiles, isect_ids, gaussian_ids):
     """Extension: stable (tile | depth) radix sort, replaces torch.sort + gather (utils.py:179-180)."""
     require_cuda(isect_ids, gaussian_ids)
-    with torch.cuda.device(isect_ids.device):
+    with on_device(isect_ids.device):
         lib = _lib.load()
         m = isect_ids.numel()
         ks, vs = torch.empty_like(isect_ids), torch.empty_like(gaussian_ids)
@@ -180,7 +180,7 @@ def sort_intersects(num_tiles, isect_ids, gaussian_ids):
 def get_tile_bin_edges(num_intersects, isect_ids_sorted, tile_bounds):
     """-> tile_bins (tiles,2) i32  [bindings.cu:404-422]"""
     require_cuda(isect_ids_sorted)
-    with torch.cuda.device(isect_ids_sorted.device):
+    with on_device(isect_ids_sorted.device):
         tiles = int(tile_bounds[0]) * int(tile_bounds[1])
         bins = torch.empty((tiles, 2), dtype=torch.int32, device=isect_ids_sorted.device)
         check(_lib.load().b200_get_tile_bin_edges(int(num_intersects), tiles, ptr(isect_ids_sorted), ptr(bins), stream()))
@@ -191,7 +191,7 @@ def cumulative_intersects(num_tiles_hit):
     """Extension: int32 inclusive scan + async read-back of the total (utils.py:123-124)."""
     require_cuda(num_tiles_hit)
     dev = num_tiles_hit.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         lib = _lib.load()
         n = num_tiles_hit.numel()
         cum = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -213,7 +213,7 @@ def bin_tiles(num_intersects, xys, depths, radii, num_tiles_hit, tile_bounds, bl
     bin_and_sort_gaussians()[3:5] (utils.py:128-182) without materialising the 64-bit keys."""
     require_cuda(xys, depths, radii, num_tiles_hit)
     dev = xys.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         lib = _lib.load()
         n, m = xys.size(0), int(num_intersects)
         tiles = int(tile_bounds[0]) * int(tile_bounds[1])
@@ -230,7 +230,7 @@ def bin_tiles(num_intersects, xys, depths, radii, num_tiles_hit, tile_bounds, bl
 def pack_records(xys, pix_vels, conics, colors, opacities):
     """Extension: the 64-byte per-Gaussian blend records (uint8 tensor of N * 64 bytes)."""
     require_cuda(xys, pix_vels, conics, colors, opacities)
-    with torch.cuda.device(xys.device):
+    with on_device(xys.device):
         n = xys.size(0)
         packed = _packed_ws(n, xys.device)
         check(_lib.load().b200_pack_records(n, ptr(_f32(xys)), ptr(_f32(pix_vels)), ptr(_f32(conics)), ptr(_f32(colors)),
@@ -244,7 +244,7 @@ def bin_cull(packed, depths, radii, num_tiles_hit, img_height, img_width, block_
     One host sync (the entry count M must be known to allocate), shared with the deferred quaternion check."""
     require_cuda(packed, depths, radii, num_tiles_hit)
     dev = depths.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         lib = _lib.load()
         n = depths.numel()
         H, W, bw, S = int(img_height), int(img_width), int(block_width), int(n_blur_samples)
@@ -277,7 +277,7 @@ def blend_forward_packed(img_height, img_width, block_width, n_blur_samples, gau
     require_cuda(gaussian_ids_sorted, tile_bins, packed, background)
     dev = packed.device
     H, W, S = int(img_height), int(img_width), int(n_blur_samples)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         out_img = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         final_Ts = torch.empty((H, W, S), dtype=torch.float32, device=dev)
         final_idx = torch.empty((H, W, S), dtype=torch.int32, device=dev)
@@ -293,7 +293,7 @@ def blend_backward_packed(num_points, img_height, img_width, block_width, n_blur
     """Extension: blend backward on prepacked records -> (v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity)."""
     require_cuda(gaussian_ids_sorted, tile_bins, packed, background)
     dev = packed.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         n = int(num_points)
         f32 = dict(dtype=torch.float32, device=dev)
         v_output, v_output_alpha = _f32(v_output).contiguous(), _f32(v_output_alpha).contiguous()
@@ -322,7 +322,7 @@ def rasterize_forward(tile_bounds, block, img_size, n_blur_samples, gaussian_ids
     H, W, bw = _geom(tile_bounds, block, img_size)
     S = int(n_blur_samples)
     dev = xys.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         n = xys.size(0)
         out_img = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         final_Ts = torch.empty((H, W, max(S, 0)), dtype=torch.float32, device=dev)
@@ -345,7 +345,7 @@ def rasterize_backward(img_height, img_width, block_width, n_blur_samples, gauss
     if colors.ndimension() != 2 or colors.size(1) != 3:
         raise RuntimeError("colors must have 2 dimensions")
     dev = xys.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         n = xys.size(0)
         f32 = dict(dtype=torch.float32, device=dev)
         v_output, v_output_alpha = _f32(v_output).contiguous(), _f32(v_output_alpha).contiguous()
@@ -370,7 +370,7 @@ def nd_rasterize_forward(tile_bounds, block, img_size, n_blur_samples, gaussian_
         raise RuntimeError("rolling shutter not supported here")
     H, W, bw = _geom(tile_bounds, block, img_size)
     dev = xys.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         n, ch = xys.size(0), colors.size(1)
         out_img = torch.empty((H, W, ch), dtype=torch.float32, device=dev)
         final_Ts = torch.empty((H, W), dtype=torch.float32, device=dev)
@@ -392,7 +392,7 @@ def nd_rasterize_backward(img_height, img_width, block_width, n_blur_samples, ga
     if rolling_shutter_time != 0:
         raise RuntimeError("rolling shutter not supported here")
     dev = xys.device
-    with torch.cuda.device(dev):
+    with on_device(dev):
         n, ch = xys.size(0), colors.size(1)
         f32 = dict(dtype=torch.float32, device=dev)
         v_output, v_output_alpha = _f32(v_output).contiguous(), _f32(v_output_alpha).contiguous()

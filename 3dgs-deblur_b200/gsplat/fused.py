@@ -60,7 +60,7 @@ class _FusedRender(Function):
         _lib.require_cuda(*tens)
         lin_d = lin.detach().reshape(-1)[:3].contiguous().float()
         ang_d = ang.detach().reshape(-1)[:3].contiguous().float()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             packed = torch.empty((n * lib.b200_packed_record_bytes(),), dtype=torch.uint8, device=dev)
             depths = torch.empty((n,), dtype=torch.float32, device=dev)
             radii = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -98,7 +98,7 @@ class _FusedRender(Function):
         if v_alpha is None:
             v_alpha = torch.zeros(H, W, **f32)
         sink = ctx.grad_sink or {}
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             if ctx.total < 1:
                 v_xy = torch.zeros(n, 2, **f32)
                 v_abs, v_pix, v_conic, v_col, v_op = torch.zeros(n, 2, **f32), torch.zeros(n, 2, **f32), torch.zeros(n, 3, **f32), torch.zeros(n, 3, **f32), torch.zeros(n, 1, **f32)

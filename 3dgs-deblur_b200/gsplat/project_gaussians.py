@@ -62,7 +62,10 @@ def project_gaussians(
 
 
 def _vel_dev(v: Tensor, device) -> Tensor:
-    return v.detach().to(device=device, dtype=torch.float32).reshape(-1)[:3].contiguous()
+    v = v.detach()
+    if v.device == device and v.dtype == torch.float32 and v.numel() == 3 and v.is_contiguous():
+        return v.view(3)  # common case: no copies, no launches
+    return v.to(device=device, dtype=torch.float32).reshape(-1)[:3].contiguous()
 
 
 class _ProjectGaussians(Function):

@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--no-vel-grad", action="store_true", help="camera velocities constant (reference CUDA-path mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--images", type=int, default=8, help="distinct training images per rank")
+    ap.add_argument("--profile", action="store_true", help="also report the summed device time of all kernels per step (CUPTI)")
     ap.add_argument("--fused", action="store_true",
                     help="render through gsplat.fused.render_gaussians (caller-modified 'next' path) instead of the drop-in operators")
     return ap.parse_args()
@@ -273,6 +274,19 @@ def run_gpu_arm(args):
     ms = float(t.item())
     value = world * 1000.0 / ms
 
+    gpu_busy = None
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+
+        nprof = 20
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for k in range(nprof):
+                trainer.train_step(cams[k % n_img], targets[k % n_img], k % n_img)
+            torch.cuda.synchronize()
+        dev_us = sum(e.device_time_total for e in prof.key_averages())
+        gpu_busy = {"kernel_ms_per_step": dev_us / nprof / 1000.0, "note": "sum of device time of every kernel in a step (CUPTI); "
+                    "ms_per_step minus this is GPU idle time (launch latency, the host sync, CPU-side Python)"}
+
     # ---- end to end: host buffers in, loss out, every step (pinned uint8 image + camera H2D, loss D2H)
     cam_host = [torch.cat([c["viewmat"].reshape(-1), c["lin_vel"], c["ang_vel"], c["cam_pos"]]).pin_memory() for c in my]
     e2e_steps = max(5, args.steps // 2)
@@ -455,6 +469,8 @@ def run_gpu_arm(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
+    if gpu_busy:
+        out["gpu_busy"] = gpu_busy
     _emit(out)
     if world > 1:
         dist.destroy_process_group()

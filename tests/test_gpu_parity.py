@@ -613,7 +613,7 @@ def test_public_rasterize_nd_channels_and_uint8_colors():
     img_u8 = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(u8), opac, d["H"], d["W"], 16, background=cu(d["background"]))
     img_f = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(u8.astype(np.float32) / 255), opac, d["H"], d["W"], 16,
                                 background=cu(d["background"]))
-    assert torch.equal(img_u8, img_f)
+    torch.testing.assert_close(img_u8, img_f, rtol=1e-6, atol=1e-6)  # torch divides by 255 as a reciprocal multiply
     # default background is ones (rasterize.py:71-74)
     img_def = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(r["colors"]), opac, d["H"], d["W"], 16)
     img_one = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(r["colors"]), opac, d["H"], d["W"], 16, background=torch.ones(3, device="cuda"))
