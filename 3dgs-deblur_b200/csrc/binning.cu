@@ -4,6 +4,10 @@
 // primitives restricted to the key bits that can be set instead of a generic 64-bit torch.sort + gather.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
 #include "blend_common.cuh"
 
 namespace b200 {
@@ -200,7 +204,6 @@ __device__ __forceinline__ bool tile_survives(const PackedGaussian &g, int tx, i
 
 // counters: [0] = sum of reserved slots (the reference's num_intersects), [1] = phantom slots,
 //           [2] = 1 if Gaussian 0 can touch tile 0, [3] = number of list entries after culling (filled later),
-//           [4] = number of 32-tile work chunks
 // Work is split into chunks of 32 candidate tiles (a screen-filling splat reserves 2500 of them, most reserve < 16):
 // one warp per chunk, chunk -> Gaussian by binary search in the chunk prefix sum, so a handful of huge splats
 // cannot serialise the pass.
@@ -242,11 +245,6 @@ __global__ void __launch_bounds__(256) cull_prep_kernel(int n, const PackedGauss
     }
 }
 
-__global__ void cull_chunk_total_kernel(int n, const int32_t *__restrict__ chunk_off, const int32_t *__restrict__ chunks,
-                                        int32_t *__restrict__ counters) {
-    counters[4] = chunk_off[n - 1] + chunks[n - 1];
-}
-
 // largest g with chunk_off[g] <= chunk (chunk_off is the exclusive scan, non-decreasing).  Warp-cooperative 32-ary
 // search: every lane probes a different position, so 300k Gaussians take 4 dependent loads instead of 19.
 __device__ __forceinline__ int chunk_owner(const int32_t *__restrict__ chunk_off, int n, int chunk, int lane) {
@@ -263,19 +261,34 @@ __device__ __forceinline__ int chunk_owner(const int32_t *__restrict__ chunk_off
     return lo;
 }
 
+// Same answer when the owner g of an earlier chunk is known: a warp walks a contiguous span of chunks, so the next
+// owner is almost always within the next 32 Gaussians -- one coalesced 128-byte probe instead of a search.
+__device__ __forceinline__ int next_owner(const int32_t *__restrict__ chunk_off, int n, int g, int chunk, int lane) {
+    const int idx = g + 1 + lane;
+    const bool ok = idx < n && __ldg(chunk_off + idx) <= chunk;
+    const int k = __popc(__ballot_sync(0xffffffffu, ok));
+    return k < 32 ? g + k : chunk_owner(chunk_off, n, chunk, lane);  // a long run of invisible Gaussians: search
+}
+
+// One warp per contiguous span of chunks.  The count pass tests every candidate tile once and keeps the 32-bit
+// survival mask of each chunk (the first `mask_cap` chunks; later ones are simply re-tested), the emit pass expands
+// the stored masks into (tile, Gaussian) entries without repeating the geometry, skipping dead chunks outright.
 template <bool EMIT>
 __global__ void __launch_bounds__(256) cull_chunks_kernel(int n, int total_entries,
                                                           const PackedGaussian *__restrict__ rec,
                                                           const int4 *__restrict__ bbox,
-                                                          const int32_t *__restrict__ chunk_off, CullGeom c,
+                                                          const int32_t *__restrict__ chunk_off,
+                                                          const int32_t *__restrict__ chunks, CullGeom c,
                                                           const int32_t *__restrict__ counters,
+                                                          uint32_t *__restrict__ masks, int mask_cap,
                                                           int32_t *__restrict__ survivors,             // count pass
-                                                          const int32_t *__restrict__ pos_of,          // emit pass
-                                                          const int32_t *__restrict__ offs, int32_t *__restrict__ cursor,
-                                                          uint32_t *__restrict__ tile_keys, int32_t *__restrict__ ids) {
+                                                          const int32_t *__restrict__ base_of,         // emit pass
+                                                          int32_t *__restrict__ cursor, uint32_t *__restrict__ tile_keys,
+                                                          int32_t *__restrict__ ids) {
     const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    const int total_chunks = counters[4];
+    const int total_chunks = __ldg(chunk_off + n - 1) + __ldg(chunks + n - 1);
     const int phantoms = counters[2] ? counters[1] : 0;
     if (EMIT) {
         for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < min(phantoms, total_entries); k += gridDim.x * blockDim.x) {
@@ -283,52 +296,78 @@ __global__ void __launch_bounds__(256) cull_chunks_kernel(int n, int total_entri
             ids[k] = 0;
         }
     }
-    for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < total_chunks; chunk += warps) {
-        const int g = chunk_owner(chunk_off, n, chunk, lane);
-        const int4 bb = bbox[g];
-        const int k = ((chunk - __ldg(chunk_off + g)) << 5) + lane;
-        bool keep = false;
-        int tx = 0, ty = 0;
-        if (k < bb.w) {
-            tx = bb.x + k % bb.z; ty = bb.y + k / bb.z;
-            keep = tile_survives(rec[g], tx, ty, c);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m == 0u) continue;
-        if (!EMIT) {
-            if (lane == 0) atomicAdd(survivors + g, __popc(m));
-        } else {
-            int base = 0;
-            if (lane == 0) base = phantoms + offs[pos_of[g]] + atomicAdd(cursor + g, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) {
-                const int dst = base + __popc(m & ((1u << lane) - 1u));
-                if (dst < total_entries) {
-                    tile_keys[dst] = (uint32_t)(ty * c.tbx + tx);
-                    ids[dst] = g;
+    const int per = (total_chunks + warps - 1) / warps;
+    const int c0 = warp * per, c1 = min(total_chunks, c0 + per);
+    int g = -1, g_first = 0, g_chunks = 0;
+    int4 bb = make_int4(0, 0, 1, 0);
+    for (int cb = c0; cb < c1; cb += 32) {
+        uint32_t stored = 0u;
+        if (EMIT && cb + lane < min(c1, mask_cap)) stored = masks[cb + lane];
+        const int ce = min(c1, cb + 32);
+        for (int chunk = cb; chunk < ce; ++chunk) {
+            const bool known = EMIT && chunk < mask_cap;  // warp-uniform
+            uint32_t m = 0u;
+            if (EMIT) {
+                m = __shfl_sync(0xffffffffu, stored, chunk - cb);
+                if (known && m == 0u) continue;
+            }
+            if (g < 0 || chunk >= g_first + g_chunks) {
+                g = g < 0 ? chunk_owner(chunk_off, n, chunk, lane) : next_owner(chunk_off, n, g, chunk, lane);
+                bb = bbox[g];
+                g_first = __ldg(chunk_off + g);
+                g_chunks = (bb.w + 31) >> 5;
+            }
+            const int k = ((chunk - g_first) << 5) + lane;
+            bool keep = false;
+            int tx = 0, ty = 0;
+            if (k < bb.w) {
+                tx = bb.x + k % bb.z; ty = bb.y + k / bb.z;
+                keep = known ? ((m >> lane) & 1u) != 0u : tile_survives(rec[g], tx, ty, c);
+            }
+            if (!known) m = __ballot_sync(0xffffffffu, keep);
+            if (!EMIT) {
+                if (lane == 0) {
+                    if (chunk < mask_cap) masks[chunk] = m;
+                    if (m) atomicAdd(survivors + g, __popc(m));
+                }
+            } else {
+                if (m == 0u) continue;
+                int base = 0;
+                if (lane == 0) {
+                    base = phantoms + base_of[g];
+                    if (g_chunks > 1) base += atomicAdd(cursor + g, __popc(m));
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) {
+                    const int dst = base + __popc(m & ((1u << lane) - 1u));
+                    if (dst < total_entries) {
+                        tile_keys[dst] = (uint32_t)(ty * c.tbx + tx);
+                        ids[dst] = g;
+                    }
                 }
             }
         }
     }
 }
 
-// survivors in depth order + the inverse permutation (Gaussian -> sorted position)
+// survivors in depth order
 __global__ void __launch_bounds__(256) gather_survivors_kernel(int n, const int32_t *__restrict__ order,
                                                                const int32_t *__restrict__ survivors,
-                                                               int32_t *__restrict__ surv_sorted,
-                                                               int32_t *__restrict__ pos_of) {
+                                                               int32_t *__restrict__ surv_sorted) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int g = order[i];
-        surv_sorted[i] = survivors[g];
-        pos_of[g] = i;
-    }
+    if (i < n) surv_sorted[i] = survivors[order[i]];
 }
 
-__global__ void cull_total_kernel(int n, const int32_t *__restrict__ offs, const int32_t *__restrict__ surv_sorted,
-                                  int32_t *__restrict__ counters) {
-    const int phantoms = counters[2] ? counters[1] : 0;
-    counters[3] = phantoms + offs[n - 1] + surv_sorted[n - 1];
+// Gaussian -> first slot of its entries (depth order), and the culled entry total for the host
+__global__ void __launch_bounds__(256) cull_finish_kernel(int n, const int32_t *__restrict__ order,
+                                                          const int32_t *__restrict__ offs,
+                                                          const int32_t *__restrict__ surv_sorted,
+                                                          int32_t *__restrict__ base_of, int32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        base_of[order[i]] = offs[i];
+        if (i == n - 1) counters[3] = (counters[2] ? counters[1] : 0) + offs[i] + surv_sorted[i];
+    }
 }
 
 static int key_end_bit(int num_tiles) {
@@ -479,9 +518,21 @@ extern "C" int b200_bin_tiles(int num_points, int num_intersects, const float *x
 // Two workspaces: a per-Gaussian one (size known up front) that carries {order, survivors, offsets, counters} from
 // the count phase to the emit phase, and a per-entry one sized after the host has read the culled entry count.
 struct CullWsG {
-    size_t keys_a, keys_b, vals_a, order, survivors, surv_sorted, offs, bbox, chunks, chunk_off, cursor, pos_of, counters,
-        cub, cub_bytes, total;
+    size_t keys_a, keys_b, vals_a, order, survivors, surv_sorted, offs, bbox, chunks, chunk_off, cursor, base_of, counters,
+        masks, cub, cub_bytes, cub_scan, cub_scan_bytes, total;
+    int mask_cap;
 };
+// Chunk masks kept between the two passes: enough for every scene whose candidate tiles average <= 128 per Gaussian
+// (BASELINE config 2: 0.5 chunks per Gaussian); beyond the cap the emit pass re-tests.  B200_CULL_MASK_CAP overrides
+// it (tests use it to exercise the re-test path).
+static int cull_mask_cap(int n) {
+    static const long long forced = [] {
+        const char *e = getenv("B200_CULL_MASK_CAP");
+        return e ? atoll(e) : -1ll;
+    }();
+    if (forced >= 0) return (int)std::min<long long>(forced, 1ll << 30);
+    return (int)std::min<long long>(4ll * n + 65536ll, 1ll << 28);
+}
 static CullWsG cull_ws_g(int n) {
     CullWsG L;
     size_t off = 0;
@@ -489,14 +540,18 @@ static CullWsG cull_ws_g(int n) {
     L.keys_a = take(4 * (size_t)n); L.keys_b = take(4 * (size_t)n); L.vals_a = take(4 * (size_t)n);
     L.order = take(4 * (size_t)n); L.survivors = take(4 * (size_t)n); L.surv_sorted = take(4 * (size_t)n);
     L.offs = take(4 * (size_t)n); L.bbox = take(16 * (size_t)n); L.chunks = take(4 * (size_t)n);
-    L.chunk_off = take(4 * (size_t)n); L.cursor = take(4 * (size_t)n); L.pos_of = take(4 * (size_t)n);
+    L.chunk_off = take(4 * (size_t)n); L.cursor = take(4 * (size_t)n); L.base_of = take(4 * (size_t)n);
     L.counters = take(256);
+    L.mask_cap = cull_mask_cap(n);
+    L.masks = take(4 * (size_t)(L.mask_cap > 0 ? L.mask_cap : 1));
     size_t b1 = 0, b3 = 0;
     cub::DeviceRadixSort::SortPairs((void *)nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32);
     cub::DeviceScan::ExclusiveSum((void *)nullptr, b3, (const int32_t *)nullptr, (int32_t *)nullptr, n);
-    L.cub_bytes = (b1 > b3 ? b1 : b3) + 256;
+    L.cub_bytes = b1 + 256;  // depth sort (side stream)
     L.cub = take(L.cub_bytes);
+    L.cub_scan_bytes = b3 + 256;  // the two scans (main stream), concurrent with the sort
+    L.cub_scan = take(L.cub_scan_bytes);
     L.total = off;
     return L;
 }
@@ -519,6 +574,30 @@ static CullWsE cull_ws_e(int m) {
 
 extern "C" size_t b200_bin_cull_ws_bytes(int num_points) { return cull_ws_g(num_points > 0 ? num_points : 1).total; }
 extern "C" size_t b200_bin_cull_emit_ws_bytes(int num_entries) { return cull_ws_e(num_entries > 0 ? num_entries : 1).total; }
+
+// One non-blocking helper stream + fork/join events per device, created on first use and kept for the process.
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static std::mutex side_mu;  // also held while a call enqueues its fork .. join section (the events are shared)
+static bool side_stream(SideStream &out) {
+    static SideStream per_dev[64];
+    static bool made[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    std::lock_guard<std::mutex> lock(side_mu);
+    if (!made[dev]) {
+        SideStream s;
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return false;
+        per_dev[dev] = s;
+        made[dev] = true;
+    }
+    out = per_dev[dev];
+    return true;
+}
 
 constexpr int CULL_GRID = 148 * 8;  // persistent warps, grid-stride over the chunk list
 
@@ -555,26 +634,38 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     const CullGeom c = make_cull_geom(img_height, img_width, block_width, n_blur_samples, rolling_shutter_time, exposure_time);
     int4 *bbox = (int4 *)(base + L.bbox);
     int32_t *chunks = (int32_t *)(base + L.chunks), *chunk_off = (int32_t *)(base + L.chunk_off);
-    int32_t *cursor = (int32_t *)(base + L.cursor), *pos_of = (int32_t *)(base + L.pos_of);
+    int32_t *cursor = (int32_t *)(base + L.cursor), *base_of = (int32_t *)(base + L.base_of);
+    uint32_t *masks = (uint32_t *)(base + L.masks);
+    void *scan_ws = base + L.cub_scan;
+    size_t scan_bytes = L.cub_scan_bytes;
     const PackedGaussian *rec = reinterpret_cast<const PackedGaussian *>(packed);
+    SideStream side;
+    B200_REQUIRE(side_stream(side), "could not create the binning side stream");
     B200_CUDA(cudaMemsetAsync(counters, 0, 256, st));
     cull_prep_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, rec, depths, radii, num_tiles_hit, c, keys_a, vals_a, bbox, chunks,
                                                        survivors, cursor, counters);
     B200_LAUNCH_CHECK();
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, chunks, chunk_off, n, st));
+    // the depth sort only needs the keys: it runs beside the scan + tile tests, both are chains of short kernels
+    {
+        std::lock_guard<std::mutex> lock(side_mu);
+        B200_CUDA(cudaEventRecord(side.fork, st));
+        B200_CUDA(cudaStreamWaitEvent(side.stream, side.fork, 0));
+        B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, order, n, 0, 32, side.stream));
+        count_launch(5);
+        B200_CUDA(cudaEventRecord(side.join, side.stream));
+    }
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, chunks, chunk_off, n, st));
     count_launch(2);
-    cull_chunk_total_kernel<<<1, 1, 0, st>>>(n, chunk_off, chunks, counters);
+    cull_chunks_kernel<false><<<CULL_GRID, 256, 0, st>>>(n, 0, rec, bbox, chunk_off, chunks, c, counters, masks, L.mask_cap,
+                                                         survivors, nullptr, nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
-    cull_chunks_kernel<false><<<CULL_GRID, 256, 0, st>>>(n, 0, rec, bbox, chunk_off, c, counters, survivors, nullptr, nullptr,
-                                                         nullptr, nullptr, nullptr);
+    // (a later record of the shared join event by another caller is ordered after this one on the side stream)
+    B200_CUDA(cudaStreamWaitEvent(st, side.join, 0));
+    gather_survivors_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, survivors, surv_sorted);
     B200_LAUNCH_CHECK();
-    B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, order, n, 0, 32, st));
-    count_launch(5);
-    gather_survivors_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, survivors, surv_sorted, pos_of);
-    B200_LAUNCH_CHECK();
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, surv_sorted, offs, n, st));
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, surv_sorted, offs, n, st));
     count_launch(2);
-    cull_total_kernel<<<1, 1, 0, st>>>(n, offs, surv_sorted, counters);
+    cull_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, offs, surv_sorted, base_of, counters);
     B200_LAUNCH_CHECK();
     B200_CUDA(cudaMemcpyAsync(totals_host_pinned, counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return B200_OK;
@@ -600,17 +691,20 @@ extern "C" int b200_bin_cull_emit(int num_points, int num_entries, const void *p
     const CullWsE E = cull_ws_e(m);
     B200_REQUIRE(ws_e_bytes >= E.total, "workspace too small: %zu < %zu", ws_e_bytes, E.total);
     const char *gb = static_cast<const char *>(ws_g);
-    const int32_t *offs = (const int32_t *)(gb + G.offs), *counters = (const int32_t *)(gb + G.counters);
+    const int32_t *counters = (const int32_t *)(gb + G.counters);
     const int4 *bbox = (const int4 *)(gb + G.bbox);
-    const int32_t *chunk_off = (const int32_t *)(gb + G.chunk_off), *pos_of = (const int32_t *)(gb + G.pos_of);
+    const int32_t *chunk_off = (const int32_t *)(gb + G.chunk_off), *base_of = (const int32_t *)(gb + G.base_of);
+    const int32_t *chunks = (const int32_t *)(gb + G.chunks);
     int32_t *cursor = (int32_t *)(const_cast<char *>(gb) + G.cursor);
+    uint32_t *masks = (uint32_t *)(const_cast<char *>(gb) + G.masks);
     char *eb = static_cast<char *>(ws_e);
     uint32_t *tkeys_a = (uint32_t *)(eb + E.tkeys_a), *tkeys_b = (uint32_t *)(eb + E.tkeys_b);
     int32_t *ids_a = (int32_t *)(eb + E.ids_a);
     void *cub_ws = eb + E.cub;
     size_t cub_bytes = E.cub_bytes;
     cull_chunks_kernel<true><<<CULL_GRID, 256, 0, st>>>(n, m, reinterpret_cast<const PackedGaussian *>(packed), bbox, chunk_off,
-                                                        c, counters, nullptr, pos_of, offs, cursor, tkeys_a, ids_a);
+                                                        chunks, c, counters, masks, G.mask_cap, nullptr, base_of, cursor,
+                                                        tkeys_a, ids_a);
     B200_LAUNCH_CHECK();
     int bits = key_end_bit(num_tiles) - 32;
     if (bits < 1) bits = 1;

@@ -26,7 +26,7 @@ struct BlendBwdParams {
     const float *final_Ts;
     const int32_t *final_idx;
     const float *v_out;        // (H,W,3)
-    const float *v_out_alpha;  // (H,W)
+    const float *v_out_alpha;  // (H,W), or null for a zero cotangent
     float *v_xy, *v_xy_abs, *v_pix_vel, *v_conic, *v_rgb, *v_opac;
 };
 
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : 3) blend_b
         vo[q][0] = vo[q][1] = vo[q][2] = 0.f;
         if (inside[q]) {
             vo[q][0] = p.v_out[3 * pix]; vo[q][1] = p.v_out[3 * pix + 1]; vo[q][2] = p.v_out[3 * pix + 2];
-            voa = p.v_out_alpha[pix];
+            voa = p.v_out_alpha ? p.v_out_alpha[pix] : 0.f;
         }
         const float bgdot = bg0 * vo[q][0] + bg1 * vo[q][1] + bg2 * vo[q][2];
 #pragma unroll
@@ -288,7 +288,7 @@ static int run_blend_backward(int num_points, unsigned img_height, unsigned img_
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
     B200_REQUIRE(img_height > 0 && img_width > 0, "image size must be positive");
     B200_REQUIRE(tile_bins && background && packed && aligned16(packed), "null / misaligned input pointer");
-    B200_REQUIRE(final_Ts && final_idx && v_output && v_output_alpha, "null saved / cotangent pointer");
+    B200_REQUIRE(final_Ts && final_idx && v_output, "null saved / cotangent pointer");
     B200_REQUIRE(v_xy && v_xy_abs && v_pix_vels && v_conic && v_colors && v_opacity, "null output pointer");
     const size_t n = (size_t)num_points;
     B200_CUDA(cudaMemsetAsync(v_xy, 0, n * 2 * sizeof(float), st));

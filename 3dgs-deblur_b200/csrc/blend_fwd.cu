@@ -23,6 +23,7 @@ struct BlendFwdParams {
     const float *background;  // device float[3]
     float *out_img;           // (H,W,3)
     float *final_Ts;          // (H,W,S)
+    float *out_alpha;         // (H,W) or null: 1 - mean_s final_T, what rasterize.py:161-163 derives with two torch ops
     int32_t *final_idx;       // (H,W,S)
 };
 
@@ -162,16 +163,18 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
     for (int q = 0; q < PPL; ++q) {
         if (!inside[q]) continue;
         const size_t pix = (size_t)pi[q] * p.g.W + pj[q];
-        float meanT = 0.f;
+        float meanT = 0.f, sumT = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             meanT += T[q][s] * inv_s;
+            sumT += T[q][s];
             p.final_Ts[pix * S + s] = T[q][s];
             p.final_idx[pix * S + s] = last[q][s];
         }
         p.out_img[3 * pix] = acc[q][0] + meanT * bg0;
         p.out_img[3 * pix + 1] = acc[q][1] + meanT * bg1;
         p.out_img[3 * pix + 2] = acc[q][2] + meanT * bg2;
+        if (p.out_alpha) p.out_alpha[pix] = 1.0f - sumT * inv_s;
     }
 }
 
@@ -195,7 +198,7 @@ extern "C" size_t b200_packed_record_bytes(void) { return sizeof(PackedGaussian)
 static int run_blend_forward(unsigned img_height, unsigned img_width, unsigned block_width, unsigned n_blur_samples,
                              const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const void *packed,
                              float rolling_shutter_time, float exposure_time, const float *background, float *out_img,
-                             float *final_Ts, int32_t *final_idx, cudaStream_t st) {
+                             float *final_Ts, int32_t *final_idx, float *out_alpha, cudaStream_t st) {
     B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");  // bindings.cu:450-452
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
     B200_REQUIRE(img_height > 0 && img_width > 0, "image size must be positive");
@@ -210,7 +213,7 @@ static int run_blend_forward(unsigned img_height, unsigned img_width, unsigned b
     p.tile_bins = reinterpret_cast<const int2 *>(tile_bins);
     p.packed = reinterpret_cast<const PackedGaussian *>(packed);
     p.background = background;
-    p.out_img = out_img; p.final_Ts = final_Ts; p.final_idx = final_idx;
+    p.out_img = out_img; p.final_Ts = final_Ts; p.final_idx = final_idx; p.out_alpha = out_alpha;
     switch (n_blur_samples) {
         case 1: return launch_fwd<1>(p, st);
         case 2: return launch_fwd<2>(p, st);
@@ -237,9 +240,9 @@ extern "C" int b200_blend_forward_packed(unsigned img_height, unsigned img_width
                                          unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
                                          const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
                                          float exposure_time, const float *background, float *out_img, float *final_Ts,
-                                         int32_t *final_idx, void *stream) {
+                                         int32_t *final_idx, float *out_alpha, void *stream) {
     return run_blend_forward(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed,
-                             rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx,
+                             rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx, out_alpha,
                              as_stream(stream));
 }
 
@@ -259,5 +262,5 @@ extern "C" int b200_rasterize_forward(int num_points, unsigned img_height, unsig
     int rc = launch_pack(num_points, xys, pix_vels, conics, colors, opacities, packed_ws, st);
     if (rc) return rc;
     return run_blend_forward(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed_ws,
-                             rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx, st);
+                             rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx, nullptr, st);
 }

@@ -40,7 +40,7 @@ SIGNATURES = {
     "b200_bin_cull_count": (_i, [_i, _p, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _sz, _p, _p]),
     "b200_bin_cull_emit": (_i, [_i, _i, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _p, _sz, _p, _p, _p]),
     "b200_pack_records": (_i, [_i, _p, _p, _p, _p, _p, _p, _p]),
-    "b200_blend_forward_packed": (_i, [_u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p]),
+    "b200_blend_forward_packed": (_i, [_u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p]),
     "b200_blend_backward_packed": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p,
                                         _p, _p, _p, _p, _p, _p, _p]),
     "b200_fused_preprocess_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _u, _u, _u,

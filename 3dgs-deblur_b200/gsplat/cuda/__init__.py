@@ -272,8 +272,9 @@ def bin_cull(packed, depths, radii, num_tiles_hit, img_height, img_width, block_
 
 
 def blend_forward_packed(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed,
-                         rolling_shutter_time, exposure_time, background):
-    """Extension: blend forward on prepacked records -> (out_img, final_Ts, final_idx)."""
+                         rolling_shutter_time, exposure_time, background, want_alpha=False):
+    """Extension: blend forward on prepacked records -> (out_img, final_Ts, final_idx[, alpha]); alpha = 1 - mean_s
+    final_Ts written by the same kernel (rasterize.py:161-163 computes it with two torch passes)."""
     require_cuda(gaussian_ids_sorted, tile_bins, packed, background)
     dev = packed.device
     H, W, S = int(img_height), int(img_width), int(n_blur_samples)
@@ -281,9 +282,13 @@ def blend_forward_packed(img_height, img_width, block_width, n_blur_samples, gau
         out_img = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         final_Ts = torch.empty((H, W, S), dtype=torch.float32, device=dev)
         final_idx = torch.empty((H, W, S), dtype=torch.int32, device=dev)
+        alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_alpha else None
         check(_lib.load().b200_blend_forward_packed(H, W, int(block_width), S, ptr(gaussian_ids_sorted), ptr(tile_bins),
                                                     ptr(packed), float(rolling_shutter_time), float(exposure_time),
-                                                    ptr(_f32(background)), ptr(out_img), ptr(final_Ts), ptr(final_idx), stream()))
+                                                    ptr(_f32(background)), ptr(out_img), ptr(final_Ts), ptr(final_idx),
+                                                    ptr(alpha), stream()))
+    if want_alpha:
+        return out_img, final_Ts, final_idx, alpha
     return out_img, final_Ts, final_idx
 
 
@@ -296,7 +301,8 @@ def blend_backward_packed(num_points, img_height, img_width, block_width, n_blur
     with on_device(dev):
         n = int(num_points)
         f32 = dict(dtype=torch.float32, device=dev)
-        v_output, v_output_alpha = _f32(v_output).contiguous(), _f32(v_output_alpha).contiguous()
+        v_output = _f32(v_output).contiguous()
+        v_output_alpha = _f32(v_output_alpha).contiguous() if v_output_alpha is not None else None
         v_xy, v_xy_abs, v_pix = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n, 2), **f32)
         v_conic, v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
         check(_lib.load().b200_blend_backward_packed(
@@ -348,7 +354,8 @@ def rasterize_backward(img_height, img_width, block_width, n_blur_samples, gauss
     with on_device(dev):
         n = xys.size(0)
         f32 = dict(dtype=torch.float32, device=dev)
-        v_output, v_output_alpha = _f32(v_output).contiguous(), _f32(v_output_alpha).contiguous()
+        v_output = _f32(v_output).contiguous()
+        v_output_alpha = _f32(v_output_alpha).contiguous() if v_output_alpha is not None else None
         v_xy, v_xy_abs, v_pix = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n, 2), **f32)
         v_conic, v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
         check(_lib.load().b200_rasterize_backward(
@@ -395,7 +402,8 @@ def nd_rasterize_backward(img_height, img_width, block_width, n_blur_samples, ga
     with on_device(dev):
         n, ch = xys.size(0), colors.size(1)
         f32 = dict(dtype=torch.float32, device=dev)
-        v_output, v_output_alpha = _f32(v_output).contiguous(), _f32(v_output_alpha).contiguous()
+        v_output = _f32(v_output).contiguous()
+        v_output_alpha = _f32(v_output_alpha).contiguous() if v_output_alpha is not None else None
         v_xy, v_xy_abs = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32)
         v_pix = torch.zeros((n, 2), **f32)
         v_conic, v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, ch), **f32), torch.empty((n, 1), **f32)

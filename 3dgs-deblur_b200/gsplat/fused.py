@@ -75,8 +75,9 @@ class _FusedRender(Function):
                 rgb = torch.ones(H, W, 3, device=dev) * bg
                 Ts = torch.zeros(H, W, S, device=dev)
                 fi = torch.zeros(H, W, S, dtype=torch.int32, device=dev)
+                alpha = 1 - Ts.mean(dim=-1)
             else:
-                rgb, Ts, fi = _C.blend_forward_packed(H, W, bw, S, ids, bins, packed, rs, ex, bg)
+                rgb, Ts, fi, alpha = _C.blend_forward_packed(H, W, bw, S, ids, bins, packed, rs, ex, bg, want_alpha=True)
         ctx.cfg, ctx.K, ctx.total = cfg, K, total
         ctx.grad_sink, ctx.info = grad_sink, info
         ctx.vel_shapes = (lin.shape, ang.shape)
@@ -84,7 +85,8 @@ class _FusedRender(Function):
                               packed, radii, ids, bins, Ts, fi)
         info["radii"] = radii
         ctx.mark_non_differentiable(radii)
-        return rgb, 1 - Ts.mean(dim=-1)
+        ctx.set_materialize_grads(False)  # an unused alpha (or rgb) arrives as None instead of a zero image
+        return rgb, alpha
 
     @staticmethod
     def backward(ctx, v_rgb, v_alpha):
@@ -95,8 +97,8 @@ class _FusedRender(Function):
         lib = _lib.load()
         n, K = means.shape[0], ctx.K
         f32 = dict(dtype=torch.float32, device=dev)
-        if v_alpha is None:
-            v_alpha = torch.zeros(H, W, **f32)
+        if v_rgb is None:
+            v_rgb = torch.zeros(H, W, 3, **f32)
         sink = ctx.grad_sink or {}
         with _lib.on_device(dev):
             if ctx.total < 1:
@@ -104,7 +106,7 @@ class _FusedRender(Function):
                 v_abs, v_pix, v_conic, v_col, v_op = torch.zeros(n, 2, **f32), torch.zeros(n, 2, **f32), torch.zeros(n, 3, **f32), torch.zeros(n, 3, **f32), torch.zeros(n, 1, **f32)
             else:
                 v_xy, v_abs, v_pix, v_conic, v_col, v_op = _C.blend_backward_packed(
-                    n, H, W, bw, S, ids, bins, packed, rs, ex, bg, Ts, fi, v_rgb.contiguous(), v_alpha.contiguous())
+                    n, H, W, bw, S, ids, bins, packed, rs, ex, bg, Ts, fi, v_rgb.contiguous(), v_alpha)
             ctx.info["absgrad"] = v_abs
             out = {}
             for name, like in (("means", means), ("log_scales", log_scales), ("quats", quats),

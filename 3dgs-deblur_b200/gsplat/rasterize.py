@@ -61,7 +61,7 @@ class _RasterizeGaussians(Function):
         img_size = (img_width, img_height, 1)
 
         three = colors.shape[-1] == 3
-        packed = None
+        packed = out_alpha = None
         if three:
             # RGB path: pack once, culled two-level binning (ONE host sync: the culled entry count), blend.  The id
             # lists hold only the (tile, Gaussian) pairs that can colour a pixel, in the reference's order; every
@@ -84,9 +84,9 @@ class _RasterizeGaussians(Function):
             final_Ts = torch.zeros(img_height, img_width, blur_samples, device=xys.device)
             final_idx = torch.zeros(img_height, img_width, blur_samples, device=xys.device)
         elif three:
-            out_img, final_Ts, final_idx = _C.blend_forward_packed(
+            out_img, final_Ts, final_idx, out_alpha = _C.blend_forward_packed(
                 img_height, img_width, block_width, blur_samples, gaussian_ids_sorted, tile_bins, packed,
-                rolling_shutter_time, exposure_time, background)
+                rolling_shutter_time, exposure_time, background, want_alpha=True)
         else:
             gaussian_ids_sorted, tile_bins = _C.bin_tiles(num_intersects, xys, depths, radii, num_tiles_hit,
                                                           tile_bounds, block_width)
@@ -104,17 +104,22 @@ class _RasterizeGaussians(Function):
         ctx.has_packed = packed is not None
         ctx.save_for_backward(gaussian_ids_sorted, tile_bins, xys, pix_vels, conics, colors, opacity, background,
                               final_Ts, final_idx, packed if packed is not None else background)
+        ctx.set_materialize_grads(False)  # an unused output's cotangent arrives as None instead of a zero image
         if return_alpha:
-            final_T_mean = final_Ts.mean(dim=-1) if final_Ts.dim() == 3 else final_Ts
-            return out_img, 1 - final_T_mean
+            if out_alpha is None:
+                final_T_mean = final_Ts.mean(dim=-1) if final_Ts.dim() == 3 else final_Ts
+                out_alpha = 1 - final_T_mean
+            return out_img, out_alpha
         return out_img
 
     @staticmethod
     def backward(ctx, v_out_img, v_out_alpha=None):
-        if v_out_alpha is None:
-            v_out_alpha = torch.zeros_like(v_out_img[..., 0])
         (gaussian_ids_sorted, tile_bins, xys, pix_vels, conics, colors, opacity, background, final_Ts,
          final_idx, packed) = ctx.saved_tensors
+        if v_out_img is None:  # only alpha was used downstream
+            v_out_img = torch.zeros(ctx.img_height, ctx.img_width, colors.shape[-1], dtype=torch.float32, device=xys.device)
+        if v_out_alpha is None and not ctx.has_packed:
+            v_out_alpha = torch.zeros_like(v_out_img[..., 0])
 
         if ctx.num_intersects < 1:
             v_xy = torch.zeros_like(xys)
@@ -127,7 +132,7 @@ class _RasterizeGaussians(Function):
             v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity = _C.blend_backward_packed(
                 xys.size(0), ctx.img_height, ctx.img_width, ctx.block_width, ctx.blur_samples, gaussian_ids_sorted,
                 tile_bins, packed, ctx.rolling_shutter_time, ctx.exposure_time, background, final_Ts, final_idx,
-                v_out_img.contiguous(), v_out_alpha.contiguous())
+                v_out_img.contiguous(), v_out_alpha)  # None = zero alpha cotangent, no (H,W) buffer is read
             v_opacity = v_opacity.reshape(opacity.shape)
         else:
             v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity = _C.nd_rasterize_backward(

@@ -286,6 +286,24 @@ def run_gpu_arm(args):
         dev_us = sum(e.device_time_total for e in prof.key_averages())
         gpu_busy = {"kernel_ms_per_step": dev_us / nprof / 1000.0, "note": "sum of device time of every kernel in a step (CUPTI); "
                     "ms_per_step minus this is GPU idle time (launch latency, the host sync, CPU-side Python)"}
+        try:  # where the GPU waits: idle gaps between consecutive device activities, keyed by the activity that follows
+            from torch.autograd import DeviceType
+
+            evs = sorted((e for e in prof.events() if e.device_type == DeviceType.CUDA),
+                         key=lambda e: e.time_range.start)
+            gaps, end = {}, None
+            for e in evs:
+                if end is not None and e.time_range.start > end:
+                    k = e.name[:60]
+                    g = gaps.setdefault(k, [0.0, 0])
+                    g[0] += e.time_range.start - end
+                    g[1] += 1
+                end = e.time_range.end if end is None else max(end, e.time_range.end)
+            top = sorted(gaps.items(), key=lambda kv: -kv[1][0])[:12]
+            gpu_busy["idle_before_us_per_step"] = {k: [round(v[0] / nprof, 1), round(v[1] / nprof, 1)] for k, v in top}
+            gpu_busy["idle_total_us_per_step"] = round(sum(v[0] for v in gaps.values()) / nprof, 1)
+        except Exception as e:  # diagnostic only
+            gpu_busy["idle_error"] = repr(e)[:200]
 
     # ---- end to end: host buffers in, loss out, every step (pinned uint8 image + camera H2D, loss D2H)
     cam_host = [torch.cat([c["viewmat"].reshape(-1), c["lin_vel"], c["ang_vel"], c["cam_pos"]]).pin_memory() for c in my]

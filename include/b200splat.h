@@ -169,14 +169,16 @@ B200_API int b200_bin_cull_emit(int num_points, int num_entries, const void *pac
                                 int32_t *gaussian_ids_sorted, int32_t *tile_bins, void *stream);
 
 /* Packed-record variants of the blend: b200_rasterize_forward/backward = b200_pack_records + these.  Lets a caller pack
- * once per render and share the records between culled binning, forward and backward. */
+ * once per render and share the records between culled binning, forward and backward.
+ * out_alpha (H,W) may be null; when given it receives 1 - mean_s final_Ts, the alpha channel gsplat/rasterize.py:161-163
+ * builds from final_Ts with two more passes.  v_output_alpha may be null (= a zero cotangent for that channel). */
 B200_API int b200_pack_records(int num_points, const float *xys, const float *pix_vels, const float *conics,
                                const float *colors, const float *opacities, void *packed, void *stream);
 B200_API int b200_blend_forward_packed(unsigned img_height, unsigned img_width, unsigned block_width,
                                        unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
                                        const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
                                        float exposure_time, const float *background, float *out_img, float *final_Ts,
-                                       int32_t *final_idx, void *stream);
+                                       int32_t *final_idx, float *out_alpha, void *stream);
 B200_API int b200_blend_backward_packed(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
                                         unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
                                         const int32_t *tile_bins, const void *packed, float rolling_shutter_time,

@@ -13,6 +13,7 @@ gsplat/tests/test_project_gaussians.py:129-136,:319-325):
   * gradients: elementwise 5e-3 relative + 1e-3 of the tensor's max magnitude (fp32 atomics in arbitrary order vs the
     oracle's fp64 sums), <= 2e-4 outliers, cosine similarity > 1 - 1e-5.
 """
+import os
 import numpy as np
 import pytest
 import torch
@@ -295,6 +296,19 @@ def test_culled_binning_changes_no_output(name, n, motion, S, rs, exposure, H, W
                                   v_out, v_alpha)
     for a, b_, k in zip(gc, gf, ["v_xy", "v_xy_abs", "v_pix_vels", "v_conic", "v_colors", "v_opacity"]):
         grad_close(a, b_.cpu().numpy(), 1e-5, k, rtol=1e-4, outliers=1e-5)  # only the atomic order differs
+
+
+def test_culled_binning_mask_cap_fallback():
+    """The count pass keeps a survival mask per 32-tile chunk for the emit pass; chunks beyond the mask capacity are
+    re-tested instead.  Re-run the culled-vs-full identity test in a process whose capacity is 7 chunks (and 0)."""
+    import subprocess
+    import sys
+    for cap in ("7", "0"):
+        env = dict(os.environ, B200_CULL_MASK_CAP=cap)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                            "test_culled_binning_changes_no_output and c4"], env=env, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_map_and_bins_golden_reference(golden):
