@@ -8,8 +8,9 @@ full_images_datamanager.py:287-304) + the DDP wrap Splatfacto cannot actually us
     floats per Gaussian at K=16) live in ONE flat fp32 buffer, their gradients in a second one;
   * every rank renders its own image of the step (rank r takes image step*R + r) through the public
     gsplat operators -- the render block of splatfacto.py:816-880 -- and back-propagates;
-  * ONE allreduce(sum) over the flat gradient buffer per step (NCCL over NVLink on GPUs, gloo in the CPU
-    tests), then the same fused Adam step on every rank, so replicas stay bit-identical;
+  * the flat gradient buffer is averaged across ranks once per step, as two contiguous slices (SH block / the rest) so
+    that the exchange overlaps the backward pass and the optimizer (NCCL over NVLink on GPUs, gloo in the CPU tests),
+    then the same fused Adam update on every rank, so replicas stay bit-identical;
   * per-camera parameters (velocities) are disjoint rows: their gradients ride in the same buffer.
 
 The densification statistics (xys.absgrad norms, visibility counts, max 2D radius;
@@ -21,7 +22,9 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
-FIELDS = (("means", 3), ("log_scales", 3), ("quats", 4), ("sh_dc", 3), ("sh_rest", None), ("opacity_logit", 1))
+# flat layout: the geometry/opacity rows (11 floats per Gaussian) and the per-camera rows first, the SH coefficients
+# (48 of the 59 floats at K = 16) last, so "everything but SH" and "SH" are each ONE contiguous slice to exchange
+FIELDS = ("means", "log_scales", "quats", "opacity_logit", "sh_dc", "sh_rest")
 
 
 class FlatGaussians:
@@ -31,36 +34,35 @@ class FlatGaussians:
         N = scene["means"].shape[0]
         K = scene["sh_rest"].shape[1] + 1
         self.N, self.K = N, K
-        widths = [3, 3, 4, 3, 3 * (K - 1), 1]
+        widths = dict(means=3, log_scales=3, quats=4, opacity_logit=1, sh_dc=3, sh_rest=3 * (K - 1))
+        shapes = dict(means=(N, 3), log_scales=(N, 3), quats=(N, 4), opacity_logit=(N, 1), sh_dc=(N, 1, 3),
+                      sh_rest=(N, K - 1, 3))
         extra = 6 * n_cameras if optimize_velocities else 0
-        total = N * sum(widths) + extra
+        total = N * sum(widths.values()) + extra
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.flat_grad = torch.zeros_like(self.flat)
         self.params: Dict[str, torch.Tensor] = {}
-        off = 0
-        src = dict(means=scene["means"], log_scales=scene["log_scales"], quats=scene["quats"], sh_dc=scene["sh_dc"],
-                   sh_rest=scene["sh_rest"], opacity_logit=scene["opacity_logit"])
-        shapes = dict(means=(N, 3), log_scales=(N, 3), quats=(N, 4), sh_dc=(N, 1, 3), sh_rest=(N, K - 1, 3),
-                      opacity_logit=(N, 1))
-        for (name, _), w in zip(FIELDS, widths):
-            view = self.flat[off:off + N * w].view(shapes[name])
-            view.copy_(src[name].to(device).reshape(shapes[name]))
-            p = view.requires_grad_(True)
-            p.grad = self.flat_grad[off:off + N * w].view(shapes[name])
-            self.params[name] = p
-            off += N * w
-        self.slices = {}
-        off2 = 0
-        for (name, _), w in zip(FIELDS, widths):
-            self.slices[name] = (off2, off2 + N * w)
-            off2 += N * w
+        self.slices: Dict[str, tuple] = {}
         self.cam_vel: Optional[torch.Tensor] = None
-        if extra:
-            view = self.flat[off:off + extra].view(n_cameras, 6)
+
+        def take(name, off, numel, shape):
+            view = self.flat[off:off + numel].view(shape)
             p = view.requires_grad_(True)
-            p.grad = self.flat_grad[off:off + extra].view(n_cameras, 6)
-            self.cam_vel = p
-        self.floats_per_gaussian = sum(widths)
+            p.grad = self.flat_grad[off:off + numel].view(shape)
+            self.slices[name] = (off, off + numel)
+            return p
+
+        off = 0
+        for name in FIELDS:
+            if name == "sh_dc" and extra:  # camera rows sit between the geometry block and the SH block
+                self.cam_vel = take("cam_vel", off, extra, (n_cameras, 6))
+                off += extra
+            self.flat[off:off + N * widths[name]].view(shapes[name]).copy_(scene[name].to(device).reshape(shapes[name]))
+            self.params[name] = take(name, off, N * widths[name], shapes[name])
+            off += N * widths[name]
+        assert off == total
+        self.sh_start = self.slices["sh_dc"][0]  # flat[sh_start:] = all SH coefficients
+        self.floats_per_gaussian = sum(widths.values())
 
     def parameters(self) -> List[torch.Tensor]:
         ps = list(self.params.values())
@@ -122,7 +124,7 @@ def render_fused(model: FlatGaussians, cam: Dict, scene: Dict, cam_index: int = 
 
 
 class ImageShardedTrainer:
-    """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient allreduce per step."""
+    """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient exchange per step."""
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True,
                  fused: bool = False):
@@ -132,22 +134,30 @@ class ImageShardedTrainer:
         self.group = group
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
-        fused = model.flat.is_cuda
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-15, fused=fused)
+        # The exchange is split where the backward pass splits: the SH coefficients are 48 of the 59 floats per Gaussian
+        # and their gradient is final as soon as the SH backward has run -- before the projection backward.  That slice
+        # of the flat gradient buffer is reduced asynchronously from a post-accumulate hook, so most of the step's
+        # exchange overlaps the rest of the backward pass; the remaining 11 floats per Gaussian (+ camera rows) follow
+        # when backward returns and overlap the Adam update of the SH block.  Two Adam instances = the same update as one
+        # (Adam is per-element), they only let the SH block step while the second exchange is still in flight.
+        fused_adam = model.flat.is_cuda
+        sh_params = [model.params["sh_dc"], model.params["sh_rest"]]
+        rest_params = [p for p in model.parameters() if all(p is not q for q in sh_params)]
+        if self.distributed:
+            self.opt_sh = torch.optim.Adam(sh_params, lr=lr, eps=1e-15, fused=fused_adam)
+            self.opt_rest = torch.optim.Adam(rest_params, lr=lr, eps=1e-15, fused=fused_adam)
+        else:  # nothing to overlap with: one multi-tensor launch
+            self.opt = torch.optim.Adam(rest_params + sh_params, lr=lr, eps=1e-15, fused=fused_adam)
         self.step_idx = 0
-        # The SH coefficients are 48 of the 59 floats per Gaussian and their gradient is final as soon as the SH
-        # backward has run -- before the projection backward.  Their slice of the flat gradient buffer is reduced
-        # asynchronously from a post-accumulate hook, so most of the step's one exchange overlaps the rest of the
-        # backward pass; the remaining 11 floats per Gaussian (+ camera rows) follow when backward returns.
         # NCCL averages in the collective itself; gloo (CPU tests) only sums, so the 1/R scale is a separate pass there
         self._avg = self.distributed and dist.get_backend(group) == "nccl"
         self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self._sh_work = None
         self._sh_seen = 0
-        lo, hi = model.slices["sh_dc"][0], model.slices["sh_rest"][1]
-        self._sh_slice = model.flat_grad[lo:hi]
-        self._rest_slices = [model.flat_grad[:lo], model.flat_grad[hi:]]
-        self.overlap_sh = bool(overlap_sh and self.distributed and not fused)  # fused: grads land in one kernel
+        self._sh_slice = model.flat_grad[model.sh_start:]
+        self._rest_slice = model.flat_grad[:model.sh_start]
+        # the fused operator writes every gradient in one kernel: nothing is final early, nothing to overlap
+        self.overlap_sh = bool(overlap_sh and self.distributed and not self.fused)
         if self.overlap_sh:
             for name in ("sh_dc", "sh_rest"):
                 model.params[name].register_post_accumulate_grad_hook(self._on_sh_grad)
@@ -161,7 +171,7 @@ class ImageShardedTrainer:
         return (step * self.world + self.rank) % n_images
 
     def train_step(self, cam: Dict, target: torch.Tensor, cam_index: int = 0):
-        """fwd + L1 loss + bwd (+ allreduce) + Adam.  Returns the (device) loss tensor; no host sync."""
+        """fwd + L1 loss + bwd (+ gradient exchange) + Adam.  Returns the (device) loss tensor; no host sync."""
         m = self.model
         if self.fused:
             if m.cam_vel is not None:
@@ -176,16 +186,18 @@ class ImageShardedTrainer:
         loss.backward()
         if self.distributed:
             # gradients of the R images are averaged (each rank's loss is a per-image mean)
-            if self._sh_work is not None:
-                for t in self._rest_slices:
-                    if t.numel():
-                        dist.all_reduce(t, op=self._op, group=self.group)
-                self._sh_work.wait()
-            else:
-                dist.all_reduce(m.flat_grad, op=self._op, group=self.group)
+            sh_work = self._sh_work or dist.all_reduce(self._sh_slice, op=self._op, group=self.group, async_op=True)
+            rest_work = dist.all_reduce(self._rest_slice, op=self._op, group=self.group, async_op=True)
+            sh_work.wait()
             if not self._avg:
-                m.flat_grad.mul_(1.0 / self.world)
-        self.opt.step()
+                self._sh_slice.mul_(1.0 / self.world)
+            self.opt_sh.step()
+            rest_work.wait()
+            if not self._avg:
+                self._rest_slice.mul_(1.0 / self.world)
+            self.opt_rest.step()
+        else:
+            self.opt.step()
         self.step_idx += 1
         self.last_xys, self.last_radii = xys, radii
         return loss

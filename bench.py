@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--images", type=int, default=8, help="distinct training images per rank")
     ap.add_argument("--profile", action="store_true", help="also report the summed device time of all kernels per step (CUPTI)")
+    ap.add_argument("--no-fused-path", action="store_true", help="skip the extra fused-operator measurement")
     ap.add_argument("--fused", action="store_true",
                     help="render through gsplat.fused.render_gaussians (caller-modified 'next' path) instead of the drop-in operators")
     return ap.parse_args()
@@ -274,6 +275,28 @@ def run_gpu_arm(args):
     ms = float(t.item())
     value = world * 1000.0 / ms
 
+    # ---- the same step through the caller-modified fused operator, reported beside the drop-in number
+    fused_path = None
+    if not args.fused and not args.no_fused_path:
+        model_f = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
+        trainer_f = ImageShardedTrainer(model_f, scene_dev, lr=1e-4, fused=True)
+        fsteps = max(20, args.steps // 4)
+        for w in range(max(3, args.warmup // 2)):
+            trainer_f.train_step(cams[w % n_img], targets[w % n_img], w % n_img)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for k in range(fsteps):
+            trainer_f.train_step(cams[k % n_img], targets[k % n_img], k % n_img)
+        f1.record()
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1) / fsteps], device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fused_path = {"value": world * 1000.0 / float(tf.item()), "unit": "images/s", "ms_per_step": float(tf.item()),
+                      "steps": fsteps, "api": "gsplat.fused.render_gaussians (raw parameters in, one operator; caller-modified)"}
+        del trainer_f, model_f
+
     gpu_busy = None
     if args.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
@@ -457,8 +480,15 @@ def run_gpu_arm(args):
             on_path = [k for k in kernels if "note" not in kernels[k] or k == "bin_cull"]
             dom = max(on_path, key=lambda k: kernels[k]["ms"])
             walk = int(((bins[:, 1] - bins[:, 0]).long().sum().item()) * 256 * S)
+            traffic, traffic_src = None, None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full captures
+            if os.path.exists(tp) and args.n is None:
+                tj = json.load(open(tp)).get(args.config, {})
+                if dom in tj:
+                    traffic, traffic_src = tj[dom]["dram_bytes"], tj[dom]["source"]
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": round(kernels[dom]["gbs"] / peak, 5), "traffic": None, "peak_source": peak_src,
+                        "frac": round(kernels[dom]["gbs"] / peak, 5), "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peak_src,
                         "note": ("blend kernels are FP32-issue/MUFU/SHFL/atomic bound, not HBM bound (SURVEY 0.5): "
                                  "pixel-Gaussian-sample evaluations upper bound per launch = %d -> %.3g eval/s" % (
                                      walk, walk / (kernels[dom]["ms"] * 1e-3))),
@@ -487,6 +517,8 @@ def run_gpu_arm(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
+    if fused_path:
+        out["fused_path"] = fused_path
     if gpu_busy:
         out["gpu_busy"] = gpu_busy
     _emit(out)

@@ -56,6 +56,17 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(model.flat) for _ in range(world)]
     dist.all_gather(gathered, model.flat)
     assert torch.equal(gathered[0], gathered[1])
+    # the overlapped exchange (SH slice reduced from the autograd hook) gives the same parameters as the plain one
+    model2 = dp.FlatGaussians(scene, "cpu", n_cameras=4, optimize_velocities=True)
+    model2.params["means"].data[0, 0] = 7.0  # same aliasing probe as the first model
+    tr2 = dp.ImageShardedTrainer(model2, scene, lr=1e-2, overlap_sh=False)
+    assert tr.overlap_sh and not tr2.overlap_sh
+    for step in range(3):
+        i = tr2.image_index(step, 4)
+        tr2.train_step(cams[i], torch.zeros(scene["H"], scene["W"], 3), i)
+    assert torch.allclose(model.flat.detach(), model2.flat.detach(), rtol=0, atol=1e-6)
+    # layout: geometry + opacity rows, camera rows, then ONE contiguous SH block at the tail
+    assert model.slices["cam_vel"] == (50 * 11, 50 * 11 + 24) and model.sh_start == 50 * 11 + 24
     # camera-velocity rows are disjoint per image: rows of images nobody rendered this step keep zero grad
     last = {(2 * world + r) % 4 for r in range(world)}
     for c in range(4):

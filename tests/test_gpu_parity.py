@@ -632,3 +632,36 @@ def test_public_rasterize_nd_channels_and_uint8_colors():
     img_def = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(r["colors"]), opac, d["H"], d["W"], 16)
     img_one = rasterize_gaussians(xys, depths, pv, radii, conics, nth, cu(r["colors"]), opac, d["H"], d["W"], 16, background=torch.ones(3, device="cuda"))
     assert torch.equal(img_def, img_one)
+
+
+def test_alpha_channel_from_the_blend_kernel_and_unused_output_cotangents():
+    """return_alpha: the blend kernel writes 1 - mean_s(final_Ts) itself (rasterize.py:161-163 builds it from final_Ts
+    with two torch passes); an output that the loss does not use arrives in backward as None and must behave exactly
+    like the zero image the reference materialises (rasterize.py:217-218)."""
+    d = scene_np("c2", n=30000, motion=True, S=5, rs=1 / 50, exposure=1 / 60, H=160, W=208)
+    r = oracle_render(d)
+    xys, depths, pv, radii, conics, nth = (cu(r["proj"][k]) for k in ("xys", "depths", "pix_vels", "radii", "conics", "num_tiles_hit"))
+    kw = dict(background=cu(d["background"]), rolling_shutter_time=d["rs"], exposure_time=d["exposure"], blur_samples=d["S"])
+    g = np.random.default_rng(9)
+    w_img = cu(g.standard_normal((d["H"], d["W"], 3)).astype(np.float32))
+    w_alpha = cu(g.standard_normal((d["H"], d["W"])).astype(np.float32))
+
+    def run(mode):
+        col, op = cu(r["colors"]).requires_grad_(True), cu(r["opac"]).requires_grad_(True)
+        x = xys.clone().requires_grad_(True)
+        img, alpha = rasterize_gaussians(x, depths, pv, radii, conics, nth, col, op, d["H"], d["W"], 16, return_alpha=True, **kw)
+        loss = {"img": (img * w_img).sum(), "img+0alpha": (img * w_img).sum() + (alpha * 0).sum(),
+                "alpha": (alpha * w_alpha).sum(), "0img+alpha": (img * 0).sum() + (alpha * w_alpha).sum()}[mode]
+        loss.backward()
+        return img.detach(), alpha.detach(), [t.grad.clone() for t in (x, col, op)]
+
+    img, alpha, g_img = run("img")
+    _, _, g_img0 = run("img+0alpha")
+    _, _, g_a = run("alpha")
+    _, _, g_a0 = run("0img+alpha")
+    # alpha against the oracle's final_Ts (same tolerance as final_Ts itself)
+    close(alpha, 1 - r["final_Ts"].mean(axis=-1), 2e-5, 1e-5, "alpha", outliers=1e-3, outlier_atol=1e-2)
+    for a, b, k in zip(g_img, g_img0, ("v_xy", "v_colors", "v_opacity")):
+        grad_close(a, b.cpu().numpy(), 1e-5, k + " (alpha unused)", rtol=1e-4, outliers=1e-5)
+    for a, b, k in zip(g_a, g_a0, ("v_xy", "v_colors", "v_opacity")):
+        grad_close(a, b.cpu().numpy(), 1e-5, k + " (image unused)", rtol=1e-4, outliers=1e-5)
