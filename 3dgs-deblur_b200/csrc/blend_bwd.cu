@@ -282,7 +282,8 @@ static int run_blend_backward(int num_points, unsigned img_height, unsigned img_
                               const void *packed, float rolling_shutter_time, float exposure_time,
                               const float *background, const float *final_Ts, const int32_t *final_idx,
                               const float *v_output, const float *v_output_alpha, float *v_xy, float *v_xy_abs,
-                              float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity, cudaStream_t st) {
+                              float *v_pix_vels, float *v_conic, float *v_colors, float *v_opacity, bool outputs_are_zero,
+                              cudaStream_t st) {
     B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");
     B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
@@ -291,12 +292,14 @@ static int run_blend_backward(int num_points, unsigned img_height, unsigned img_
     B200_REQUIRE(final_Ts && final_idx && v_output, "null saved / cotangent pointer");
     B200_REQUIRE(v_xy && v_xy_abs && v_pix_vels && v_conic && v_colors && v_opacity, "null output pointer");
     const size_t n = (size_t)num_points;
-    B200_CUDA(cudaMemsetAsync(v_xy, 0, n * 2 * sizeof(float), st));
-    B200_CUDA(cudaMemsetAsync(v_xy_abs, 0, n * 2 * sizeof(float), st));
-    B200_CUDA(cudaMemsetAsync(v_pix_vels, 0, n * 2 * sizeof(float), st));
-    B200_CUDA(cudaMemsetAsync(v_conic, 0, n * 3 * sizeof(float), st));
-    B200_CUDA(cudaMemsetAsync(v_colors, 0, n * 3 * sizeof(float), st));
-    B200_CUDA(cudaMemsetAsync(v_opacity, 0, n * sizeof(float), st));
+    if (!outputs_are_zero) {
+        B200_CUDA(cudaMemsetAsync(v_xy, 0, n * 2 * sizeof(float), st));
+        B200_CUDA(cudaMemsetAsync(v_xy_abs, 0, n * 2 * sizeof(float), st));
+        B200_CUDA(cudaMemsetAsync(v_pix_vels, 0, n * 2 * sizeof(float), st));
+        B200_CUDA(cudaMemsetAsync(v_conic, 0, n * 3 * sizeof(float), st));
+        B200_CUDA(cudaMemsetAsync(v_colors, 0, n * 3 * sizeof(float), st));
+        B200_CUDA(cudaMemsetAsync(v_opacity, 0, n * sizeof(float), st));
+    }
     BlendBwdParams p;
     p.g = BlendGeom{(int)img_height, (int)img_width, (int)block_width,
                     (int)((img_width + block_width - 1) / block_width),
@@ -328,11 +331,11 @@ extern "C" int b200_blend_backward_packed(int num_points, unsigned img_height, u
                                           float exposure_time, const float *background, const float *final_Ts,
                                           const int32_t *final_idx, const float *v_output, const float *v_output_alpha,
                                           float *v_xy, float *v_xy_abs, float *v_pix_vels, float *v_conic,
-                                          float *v_colors, float *v_opacity, void *stream) {
+                                          float *v_colors, float *v_opacity, int outputs_are_zero, void *stream) {
     return run_blend_backward(num_points, img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted,
                               tile_bins, packed, rolling_shutter_time, exposure_time, background, final_Ts, final_idx,
                               v_output, v_output_alpha, v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity,
-                              as_stream(stream));
+                              outputs_are_zero != 0, as_stream(stream));
 }
 
 extern "C" int b200_rasterize_backward(int num_points, unsigned img_height, unsigned img_width, unsigned block_width,
@@ -353,5 +356,5 @@ extern "C" int b200_rasterize_backward(int num_points, unsigned img_height, unsi
     if (rc) return rc;
     return run_blend_backward(num_points, img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted,
                               tile_bins, packed_ws, rolling_shutter_time, exposure_time, background, final_Ts, final_idx,
-                              v_output, v_output_alpha, v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity, st);
+                              v_output, v_output_alpha, v_xy, v_xy_abs, v_pix_vels, v_conic, v_colors, v_opacity, false, st);
 }

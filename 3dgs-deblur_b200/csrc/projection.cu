@@ -228,9 +228,14 @@ extern "C" int b200_project_gaussians_backward(int num_points, const float *mean
     B200_REQUIRE(v_mean3d && v_scale && v_quat, "null gradient output pointer");
     B200_REQUIRE(aligned16(v_quat), "v_quat must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
-    if (v_lin_vel) B200_CUDA(cudaMemsetAsync(v_lin_vel, 0, 3 * sizeof(float), st));
-    if (v_ang_vel) B200_CUDA(cudaMemsetAsync(v_ang_vel, 0, 3 * sizeof(float), st));
-    if (v_viewmat) B200_CUDA(cudaMemsetAsync(v_viewmat, 0, 12 * sizeof(float), st));
+    if (v_lin_vel && v_ang_vel == v_lin_vel + 3 && (!v_viewmat || v_viewmat == v_lin_vel + 6)) {
+        // the three accumulators are one 6- or 18-float block (what gsplat/cuda allocates): one memset
+        B200_CUDA(cudaMemsetAsync(v_lin_vel, 0, (v_viewmat ? 18 : 6) * sizeof(float), st));
+    } else {
+        if (v_lin_vel) B200_CUDA(cudaMemsetAsync(v_lin_vel, 0, 3 * sizeof(float), st));
+        if (v_ang_vel) B200_CUDA(cudaMemsetAsync(v_ang_vel, 0, 3 * sizeof(float), st));
+        if (v_viewmat) B200_CUDA(cudaMemsetAsync(v_viewmat, 0, 12 * sizeof(float), st));
+    }
     ProjBwdIO io{cov3d, conics, compensation, radii, v_xy, v_depth, v_pix_vel, v_conic, v_compensation,
                  v_cov2d, v_cov3d, v_mean3d, v_scale, v_quat, v_lin_vel, v_ang_vel, v_viewmat};
     const int blocks = ceil_div(num_points, PROJ_THREADS);

@@ -42,7 +42,7 @@ SIGNATURES = {
     "b200_pack_records": (_i, [_i, _p, _p, _p, _p, _p, _p, _p]),
     "b200_blend_forward_packed": (_i, [_u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p]),
     "b200_blend_backward_packed": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p,
-                                        _p, _p, _p, _p, _p, _p, _p]),
+                                        _p, _p, _p, _p, _p, _p, _i, _p]),
     "b200_fused_preprocess_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _u, _u, _u,
                                            _f, _p, _p, _p, _p, _p]),
     "b200_fused_preprocess_backward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _u, _u,
@@ -50,6 +50,8 @@ SIGNATURES = {
     "b200_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_l1_loss_ws_bytes": (_sz, []),
+    "b200_l1_loss": (_i, [C.c_longlong, _p, _p, _p, _p, _p, _i, _p]),
     "b200_nd_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_nd_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                         _p, _p, _p, _p, _p, _p]),

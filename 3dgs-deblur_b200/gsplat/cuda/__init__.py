@@ -86,9 +86,14 @@ def project_gaussians_backward(num_points, means3d, scales, glob_scale, quats, l
         v_mean3d = torch.empty((n, 3), **f32)
         v_scale = torch.empty((n, 3), **f32)
         v_quat = torch.empty((n, 4), **f32)
-        v_lin = torch.empty(3, **f32) if _want_vel else None
-        v_ang = torch.empty(3, **f32) if _want_vel else None
-        v_vm = torch.empty((3, 4), **f32) if _want_viewmat else None
+        v_lin = v_ang = v_vm = None
+        if _want_vel:  # one block for the 6 (+12) accumulators: the library clears it with a single memset
+            acc = torch.empty(18 if _want_viewmat else 6, **f32)
+            v_lin, v_ang = acc[0:3], acc[3:6]
+            if _want_viewmat:
+                v_vm = acc[6:18].view(3, 4)
+        elif _want_viewmat:
+            v_vm = torch.empty((3, 4), **f32)
         check(_lib.load().b200_project_gaussians_backward(
             n, ptr(_f32(means3d)), ptr(_f32(scales)), float(glob_scale), ptr(_f32(quats)), ptr(lin), ptr(ang),
             float(rolling_shutter_time), float(exposure_time), ptr(_f32(viewmat)), float(fx), float(fy), float(cx),
@@ -303,13 +308,18 @@ def blend_backward_packed(num_points, img_height, img_width, block_width, n_blur
         f32 = dict(dtype=torch.float32, device=dev)
         v_output = _f32(v_output).contiguous()
         v_output_alpha = _f32(v_output_alpha).contiguous() if v_output_alpha is not None else None
-        v_xy, v_xy_abs, v_pix = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n, 2), **f32)
-        v_conic, v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
+        # one zero-filled allocation for the 13 floats per Gaussian the kernel accumulates into (each array 64-byte
+        # aligned inside it): one fill instead of six memsets
+        pitch = (n + 15) & ~15
+        acc = torch.zeros(13 * pitch, **f32)
+        v_xy, v_xy_abs, v_pix = (acc[k * 2 * pitch:k * 2 * pitch + 2 * n].view(n, 2) for k in range(3))
+        v_conic, v_colors = (acc[6 * pitch + k * 3 * pitch:6 * pitch + k * 3 * pitch + 3 * n].view(n, 3) for k in range(2))
+        v_opacity = acc[12 * pitch:12 * pitch + n].view(n, 1)
         check(_lib.load().b200_blend_backward_packed(
             n, int(img_height), int(img_width), int(block_width), int(n_blur_samples), ptr(gaussian_ids_sorted),
             ptr(tile_bins), ptr(packed), float(rolling_shutter_time), float(exposure_time), ptr(_f32(background)),
             ptr(_f32(final_Ts)), ptr(final_idx), ptr(v_output), ptr(v_output_alpha), ptr(v_xy), ptr(v_xy_abs), ptr(v_pix),
-            ptr(v_conic), ptr(v_colors), ptr(v_opacity), stream()))
+            ptr(v_conic), ptr(v_colors), ptr(v_opacity), 1, stream()))
     return v_xy, v_xy_abs, v_pix, v_conic, v_colors, v_opacity
 
 

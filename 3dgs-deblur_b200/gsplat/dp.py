@@ -127,8 +127,11 @@ class ImageShardedTrainer:
     """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient exchange per step."""
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True,
-                 fused: bool = False):
+                 fused: bool = False, loss_fn=None):
         self.model, self.scene = model, scene
+        if loss_fn is None:  # fused L1 (value + cotangent in one kernel); CUDA only, like the operators themselves
+            from gsplat.losses import l1_loss as loss_fn
+        self.loss_fn = loss_fn
         self.fused = fused  # render through gsplat.fused (caller-modified path) instead of the three drop-in operators
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.group = group
@@ -181,7 +184,7 @@ class ImageShardedTrainer:
         else:
             m.zero_grad()
             rgb, alpha, xys, radii = render(m, cam, self.scene, cam_index)
-        loss = (rgb - target).abs().mean()
+        loss = self.loss_fn(rgb, target)
         self._sh_seen, self._sh_work = 0, None
         loss.backward()
         if self.distributed:

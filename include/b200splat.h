@@ -171,7 +171,9 @@ B200_API int b200_bin_cull_emit(int num_points, int num_entries, const void *pac
 /* Packed-record variants of the blend: b200_rasterize_forward/backward = b200_pack_records + these.  Lets a caller pack
  * once per render and share the records between culled binning, forward and backward.
  * out_alpha (H,W) may be null; when given it receives 1 - mean_s final_Ts, the alpha channel gsplat/rasterize.py:161-163
- * builds from final_Ts with two more passes.  v_output_alpha may be null (= a zero cotangent for that channel). */
+ * builds from final_Ts with two more passes.  v_output_alpha may be null (= a zero cotangent for that channel).
+ * outputs_are_zero != 0: the six gradient arrays were already cleared by the caller (e.g. carved from one zero-filled
+ * allocation), so the six memsets that otherwise precede the kernel are skipped. */
 B200_API int b200_pack_records(int num_points, const float *xys, const float *pix_vels, const float *conics,
                                const float *colors, const float *opacities, void *packed, void *stream);
 B200_API int b200_blend_forward_packed(unsigned img_height, unsigned img_width, unsigned block_width,
@@ -185,7 +187,7 @@ B200_API int b200_blend_backward_packed(int num_points, unsigned img_height, uns
                                         float exposure_time, const float *background, const float *final_Ts,
                                         const int32_t *final_idx, const float *v_output, const float *v_output_alpha,
                                         float *v_xy, float *v_xy_abs, float *v_pix_vels, float *v_conic,
-                                        float *v_colors, float *v_opacity, void *stream);
+                                        float *v_colors, float *v_opacity, int outputs_are_zero, void *stream);
 
 /* ---- blend (blur + rolling shutter), 3 channels ------------------------------------------
  * replaces rasterize_forward_tensor (bindings.h:110-127, bindings.cu:424-503; kernel forward.cu:306-456).
@@ -254,6 +256,17 @@ B200_API int b200_nd_rasterize_backward(int num_points, unsigned img_height, uns
                                const float *background, const float *final_Ts, const int32_t *final_idx,
                                const float *v_output, const float *v_output_alpha, float *v_xy, float *v_xy_abs,
                                float *v_conic, float *v_colors, float *v_opacity, void *stream);
+
+/* ---- photometric loss ("next" row f-3 of SURVEY section 8) -----------------------------------
+ * Fused L1: loss[0] = mean |pred - target| over numel floats and, when grad is not null, grad = sign(pred - target) /
+ * numel -- the cotangent rasterize_backward consumes -- in ONE pass; replaces the L1 term of the caller's loss
+ * (nerfstudio/models/splatfacto.py:957, `torch.abs(gt_img - pred_img).mean()`) and its autograd chain.
+ * ws: b200_l1_loss_ws_bytes() bytes of device scratch, 16-byte aligned, one per concurrent stream; pass
+ * ws_is_zeroed = 1 if its first 4 bytes are zero (they are left zero on return), else they are cleared here.
+ * Deterministic (block partial sums are added in block order). */
+B200_API size_t b200_l1_loss_ws_bytes(void);
+B200_API int b200_l1_loss(long long numel, const float *pred, const float *target, float *loss, float *grad, void *ws,
+                          int ws_is_zeroed, void *stream);
 
 #ifdef __cplusplus
 }
