@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 
 #include "blend_common.cuh"
@@ -155,6 +156,36 @@ __global__ void __launch_bounds__(256) tile_bin_edges32_kernel(int m, const uint
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// cub's temp-size queries run its whole dispatch prologue (device / occupancy attribute look-ups); the culled path
+// asks for the same sizes every step, right after its host sync while the GPU is waiting.  Sizes are memoised per item
+// count, counts rounded up to 64 Ki items (temp storage grows with the item count, so the rounded size is sufficient).
+static int round_items(int n) { return n <= 0 ? 65536 : (int)std::min<long long>(((long long)n + 65535) & ~65535ll, 0x7fffffffll); }
+static size_t sort32_temp_bytes(int n) {
+    static std::mutex mu;
+    static std::map<int, size_t> memo;
+    const int key = round_items(n);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, key, 0, 32);
+    if (b) memo[key] = b;  // (0 = no device: do not cache)
+    return b;
+}
+static size_t scan32_temp_bytes(int n) {
+    static std::mutex mu;
+    static std::map<int, size_t> memo;
+    const int key = round_items(n);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+    size_t b = 0;
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, b, (const int32_t *)nullptr, (int32_t *)nullptr, key);
+    if (b) memo[key] = b;
+    return b;
+}
+
 struct BinTilesLayout {
     size_t keys_a, keys_b, vals_a, vals_b, emitted, emitted_sorted, offs, tkeys_a, tkeys_b, ids_a, cub, cub_bytes, total;
 };
@@ -167,12 +198,7 @@ static BinTilesLayout bin_tiles_layout(int n, int m) {
     L.vals_a = take(4 * (size_t)n); L.vals_b = take(4 * (size_t)n);
     L.emitted = take(4 * (size_t)n); L.emitted_sorted = take(4 * (size_t)n); L.offs = take(4 * (size_t)n);
     L.tkeys_a = take(4 * (size_t)m); L.tkeys_b = take(4 * (size_t)m); L.ids_a = take(4 * (size_t)m);
-    size_t b1 = 0, b2 = 0, b3 = 0;
-    cub::DeviceRadixSort::SortPairs((void *)nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32);
-    cub::DeviceRadixSort::SortPairs((void *)nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const int32_t *)nullptr, (int32_t *)nullptr, m > 0 ? m : 1, 0, 32);
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, b3, (const int32_t *)nullptr, (int32_t *)nullptr, n);
+    const size_t b1 = sort32_temp_bytes(n), b2 = sort32_temp_bytes(m > 0 ? m : 1), b3 = scan32_temp_bytes(n);
     L.cub_bytes = b1 > b2 ? (b1 > b3 ? b1 : b3) : (b2 > b3 ? b2 : b3);
     L.cub = take(L.cub_bytes + 256);
     L.total = off;
@@ -362,11 +388,15 @@ __global__ void __launch_bounds__(256) gather_survivors_kernel(int n, const int3
 __global__ void __launch_bounds__(256) cull_finish_kernel(int n, const int32_t *__restrict__ order,
                                                           const int32_t *__restrict__ offs,
                                                           const int32_t *__restrict__ surv_sorted,
-                                                          int32_t *__restrict__ base_of, int32_t *__restrict__ counters) {
+                                                          int32_t *__restrict__ base_of, int32_t *__restrict__ counters,
+                                                          const int32_t *__restrict__ flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         base_of[order[i]] = offs[i];
-        if (i == n - 1) counters[3] = (counters[2] ? counters[1] : 0) + offs[i] + surv_sorted[i];
+        if (i == n - 1) {
+            counters[3] = (counters[2] ? counters[1] : 0) + offs[i] + surv_sorted[i];
+            counters[4] = flag ? *flag : 0;  // deferred input-check word rides along with the totals
+        }
     }
 }
 
@@ -544,10 +574,7 @@ static CullWsG cull_ws_g(int n) {
     L.counters = take(256);
     L.mask_cap = cull_mask_cap(n);
     L.masks = take(4 * (size_t)(L.mask_cap > 0 ? L.mask_cap : 1));
-    size_t b1 = 0, b3 = 0;
-    cub::DeviceRadixSort::SortPairs((void *)nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const int32_t *)nullptr, (int32_t *)nullptr, n, 0, 32);
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, b3, (const int32_t *)nullptr, (int32_t *)nullptr, n);
+    const size_t b1 = sort32_temp_bytes(n), b3 = scan32_temp_bytes(n);
     L.cub_bytes = b1 + 256;  // depth sort (side stream)
     L.cub = take(L.cub_bytes);
     L.cub_scan_bytes = b3 + 256;  // the two scans (main stream), concurrent with the sort
@@ -563,9 +590,7 @@ static CullWsE cull_ws_e(int m) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
     L.tkeys_a = take(4 * (size_t)m); L.tkeys_b = take(4 * (size_t)m); L.ids_a = take(4 * (size_t)m);
-    size_t b2 = 0;
-    cub::DeviceRadixSort::SortPairs((void *)nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const int32_t *)nullptr, (int32_t *)nullptr, m, 0, 32);
+    const size_t b2 = sort32_temp_bytes(m);
     L.cub_bytes = b2 + 256;
     L.cub = take(L.cub_bytes);
     L.total = off;
@@ -614,7 +639,7 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
                                    const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
                                    unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
                                    float exposure_time, void *ws_g, size_t ws_g_bytes, int32_t *totals_host_pinned,
-                                   void *stream) {
+                                   const int32_t *flag_dev, void *stream) {
     B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
     B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");
@@ -665,9 +690,9 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     B200_LAUNCH_CHECK();
     B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, surv_sorted, offs, n, st));
     count_launch(2);
-    cull_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, offs, surv_sorted, base_of, counters);
+    cull_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, offs, surv_sorted, base_of, counters, flag_dev);
     B200_LAUNCH_CHECK();
-    B200_CUDA(cudaMemcpyAsync(totals_host_pinned, counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(totals_host_pinned, counters, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return B200_OK;
 }
 

@@ -37,7 +37,7 @@ SIGNATURES = {
     "b200_bin_tiles": (_i, [_i, _i, _p, _p, _p, _p, _u, _u, _u, _p, _sz, _p, _p, _p]),
     "b200_bin_cull_ws_bytes": (_sz, [_i]),
     "b200_bin_cull_emit_ws_bytes": (_sz, [_i]),
-    "b200_bin_cull_count": (_i, [_i, _p, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _sz, _p, _p]),
+    "b200_bin_cull_count": (_i, [_i, _p, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _sz, _p, _p, _p]),
     "b200_bin_cull_emit": (_i, [_i, _i, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _p, _sz, _p, _p, _p]),
     "b200_pack_records": (_i, [_i, _p, _p, _p, _p, _p, _p, _p]),
     "b200_blend_forward_packed": (_i, [_u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p]),
@@ -134,11 +134,17 @@ def require_cuda(*tensors):
 # Set B200SPLAT_SYNC_CHECKS=1 to get the reference's immediate (synchronising) behaviour.
 SYNC_CHECKS = os.environ.get("B200SPLAT_SYNC_CHECKS", "0") == "1"
 _pending_flags = {}   # device index -> int32 device tensor awaiting a read-back
+_quat_flags = {}      # device index -> the device's persistent (sticky) flag word: zero unless a check has failed
+_host_scratch_np = {}
 _host_scratch = {}    # device index -> pinned int32[8]: [0] total, [1] flag (scan path); [0:4] totals, [4] flag (cull path)
 
 
 def new_quat_flag(device):
-    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    """The device's sticky flag word (kernels only ever OR into it, so no per-call clear is needed), marked pending."""
+    flag = _quat_flags.get(device.index)
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        _quat_flags[device.index] = flag
     _pending_flags[device.index] = flag
     return flag
 
@@ -152,9 +158,19 @@ def host_scratch(device):
     if buf is None:
         buf = torch.zeros(8, dtype=torch.int32).pin_memory()
         _host_scratch[device.index] = buf
+        _host_scratch_np[device.index] = (buf.data_ptr(), buf.numpy())
     return buf
+
+
+def host_scratch_np(device):
+    """(address, numpy view) of the pinned scratch: reads after the host sync cost ~0.1 us instead of a tensor index."""
+    if device.index not in _host_scratch_np:
+        host_scratch(device)
+    return _host_scratch_np[device.index]
 
 
 def raise_if_flagged(flag_value):
     if int(flag_value) != 0:
+        for flag in _quat_flags.values():  # re-arm (rare path)
+            flag.zero_()
         raise AssertionError("quats must be normalized")  # deferred project_gaussians.py:69

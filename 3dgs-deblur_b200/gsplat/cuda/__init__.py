@@ -256,19 +256,18 @@ def bin_cull(packed, depths, radii, num_tiles_hit, img_height, img_width, block_
         rs, ex = float(rolling_shutter_time), float(exposure_time)
         ws_bytes = lib.b200_bin_cull_ws_bytes(n)
         ws_g = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        host = _lib.host_scratch(dev)
-        check(lib.b200_bin_cull_count(n, ptr(packed), ptr(_f32(depths)), ptr(radii), ptr(num_tiles_hit), H, W, bw, S, rs, ex,
-                                      ptr(ws_g), ws_bytes, host.data_ptr(), stream()))
+        host_ptr, host = _lib.host_scratch_np(dev)
         flag = _lib.take_pending_flag(dev)
-        if flag is not None:
-            host[4:5].copy_(flag, non_blocking=True)
+        tiles = ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
+        bins = torch.empty((tiles, 2), dtype=torch.int32, device=dev)
+        check(lib.b200_bin_cull_count(n, ptr(packed), ptr(_f32(depths)), ptr(radii), ptr(num_tiles_hit), H, W, bw, S, rs, ex,
+                                      ptr(ws_g), ws_bytes, host_ptr, ptr(flag), stream()))
         torch.cuda.current_stream().synchronize()  # the one host sync of the path
-        if flag is not None:
+        # (the GPU idles from here until the emit kernels are queued: keep this stretch short)
+        if host[4]:
             _lib.raise_if_flagged(host[4])
         total_ref, m = int(host[0]), int(host[3])
-        tiles = ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
         ids = torch.empty((m,), dtype=torch.int32, device=dev)
-        bins = torch.empty((tiles, 2), dtype=torch.int32, device=dev)
         e_bytes = lib.b200_bin_cull_emit_ws_bytes(m)
         ws_e = torch.empty((e_bytes,), dtype=torch.uint8, device=dev)
         check(lib.b200_bin_cull_emit(n, m, ptr(packed), ptr(radii), ptr(num_tiles_hit), H, W, bw, S, rs, ex, ptr(ws_g), ptr(ws_e),

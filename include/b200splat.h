@@ -149,9 +149,11 @@ B200_API int b200_bin_tiles(int num_points, int num_intersects, const float *xys
  * if the Gaussian can reach alpha >= 1/255 inside that tile for some blur sample; dropped pairs cannot change any pixel,
  * survivors keep the reference's order, and the reference's phantom copies of Gaussian 0 survive iff it can touch
  * tile 0.  Two calls around ONE host sync:
- *   b200_bin_cull_count: per-Gaussian survivor counts, depth sort, offsets; totals_host_pinned[4] (HOST, pinned,
- *       async) = {sum(num_tiles_hit) i.e. the reference's num_intersects, phantom slots, Gaussian-0-touches-tile-0,
- *       culled entry count M};
+ *   b200_bin_cull_count: per-Gaussian survivor counts (the 32-bit survival mask of every 32-tile chunk is kept for the
+ *       emit pass), depth sort on a helper stream, offsets; totals_host_pinned[5] (HOST, pinned, async) =
+ *       {sum(num_tiles_hit) i.e. the reference's num_intersects, phantom slots, Gaussian-0-touches-tile-0, culled
+ *       entry count M, *flag_dev (0 if flag_dev is null: the deferred input-check word of
+ *       b200_project_gaussians_forward rides along with the totals)};
  *   b200_bin_cull_emit: after the caller synchronised and allocated M ids -> gaussian_ids_sorted (M), tile_bins.
  * `packed` = records from b200_pack_records; ws_g (b200_bin_cull_ws_bytes(N) bytes) must stay alive and untouched
  * between the two calls; ws_e has b200_bin_cull_emit_ws_bytes(M) bytes; both 256-byte aligned. */
@@ -161,7 +163,7 @@ B200_API int b200_bin_cull_count(int num_points, const void *packed, const float
                                  const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
                                  unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
                                  float exposure_time, void *ws_g, size_t ws_g_bytes, int32_t *totals_host_pinned,
-                                 void *stream);
+                                 const int32_t *flag_dev, void *stream);
 B200_API int b200_bin_cull_emit(int num_points, int num_entries, const void *packed, const int32_t *radii,
                                 const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
                                 unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
