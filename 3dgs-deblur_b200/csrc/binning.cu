@@ -216,8 +216,45 @@ static BinTilesLayout bin_tiles_layout(int n, int m) {
 struct CullGeom {
     int H, W, bw, tbx, tby, S;
     float rs_time, exposure, inv_H, roll_eps;
+    int per_sample;  // 1: test the S samples one by one (B200_CULL_PER_SAMPLE=1; the tests compare both)
 };
 
+// Closed-form version of may_touch_rect for the S equally spaced blur samples b_k = (k/(S-1) - 1/2) * exposure: the
+// per-sample test "centre segment over [b_k + r0, b_k + r1], inflated by (hx, hy), meets the rectangle" holds in x iff
+// [b_k + r0, b_k + r1] meets Tx = {t : x + t vx in [x0 - hx, x1 + hx]} and likewise in y, i.e. iff
+// b_k in [max(Tx.lo, Ty.lo) - r1, min(Tx.hi, Ty.hi) - r0]; so one interval test on k replaces the loop over samples.
+// Every bound is pushed outwards (0.01 px, 1e-5 relative in time, 1e-3 of a sample step) so the kept set is a superset
+// of the per-sample test's -- extra pairs only cost time, the blend repeats the exact tests -- and NaNs keep the pair.
+__device__ __forceinline__ void time_window(float c, float v, float lo, float hi, float &t_lo, float &t_hi) {
+    const float a = lo - c - 0.01f, b = hi - c + 0.01f;  // allowed range of t * v
+    if (v == 0.f) {
+        const bool ok = !(a > 0.f) && !(b < 0.f);
+        t_lo = ok ? -INFINITY : INFINITY;
+        t_hi = ok ? INFINITY : -INFINITY;
+        return;
+    }
+    const float iv = 1.0f / v;
+    const float p = a * iv, q = b * iv;
+    t_lo = fminf(p, q); t_hi = fmaxf(p, q);
+    t_lo -= 1e-5f * fabsf(t_lo) + 1e-9f;
+    t_hi += 1e-5f * fabsf(t_hi) + 1e-9f;
+}
+
+__device__ __forceinline__ bool may_touch_rect_closed_form(const PackedGaussian &g, float x0, float x1, float y0, float y1,
+                                                           float r0, float r1, float exposure, int S) {
+    if (g.hx < 0.f) return false;
+    float xl, xh, yl, yh;
+    time_window(g.x, g.vx, x0 - g.hx, x1 + g.hx, xl, xh);
+    time_window(g.y, g.vy, y0 - g.hy, y1 + g.hy, yl, yh);
+    const float L = fmaxf(xl, yl) - r1, U = fminf(xh, yh) - r0;  // admissible blur offsets b
+    if (S == 1 || !(exposure > 0.f)) return !(L > 0.f) && !(U < 0.f);
+    const float k_per_s = (float)(S - 1) / exposure;
+    const float u = (L * k_per_s + 0.5f * (float)(S - 1)) - 1e-3f, w = (U * k_per_s + 0.5f * (float)(S - 1)) + 1e-3f;
+    const float k_lo = ceilf(fmaxf(u, 0.f)), k_hi = floorf(fminf(w, (float)(S - 1)));
+    return !(k_lo > k_hi);
+}
+
+template <bool PER_SAMPLE>
 __device__ __forceinline__ bool tile_survives(const PackedGaussian &g, int tx, int ty, const CullGeom &c) {
     const float x0 = (float)(tx * c.bw) + 0.5f, x1 = (float)min(c.W, (tx + 1) * c.bw) - 0.5f;
     const float y0 = (float)(ty * c.bw) + 0.5f, y1 = (float)min(c.H, (ty + 1) * c.bw) - 0.5f;
@@ -225,7 +262,9 @@ __device__ __forceinline__ bool tile_survives(const PackedGaussian &g, int tx, i
     // (forward.cu:360); here fp32 plus a margin of a few ulps of |rs_time| keeps the window conservative
     // without touching the (vestigial on B200) fp64 pipe once per (tile, Gaussian) pair.
     const float ra = c.rs_time * (y0 * c.inv_H - 0.5f), rb = c.rs_time * (y1 * c.inv_H - 0.5f);
-    return may_touch_rect(g, x0, x1, y0, y1, fminf(ra, rb) - c.roll_eps, fmaxf(ra, rb) + c.roll_eps, c.exposure, c.S);
+    const float r0 = fminf(ra, rb) - c.roll_eps, r1 = fmaxf(ra, rb) + c.roll_eps;
+    if (PER_SAMPLE) return may_touch_rect(g, x0, x1, y0, y1, r0, r1, c.exposure, c.S);
+    return may_touch_rect_closed_form(g, x0, x1, y0, y1, r0, r1, c.exposure, c.S);
 }
 
 // counters: [0] = sum of reserved slots (the reference's num_intersects), [1] = phantom slots,
@@ -261,7 +300,7 @@ __global__ void __launch_bounds__(256) cull_prep_kernel(int n, const PackedGauss
         keys[g] = emitted_ref > 0 ? (uint32_t)__float_as_int(depths[g]) : 0xffffffffu;
         vals[g] = g;
         phantom = max(0, reserved - emitted_ref);
-        if (g == 0) counters[2] = tile_survives(rec[0], 0, 0, c) ? 1 : 0;
+        if (g == 0) counters[2] = (c.per_sample ? tile_survives<true>(rec[0], 0, 0, c) : tile_survives<false>(rec[0], 0, 0, c)) ? 1 : 0;
     }
     reserved = __reduce_add_sync(0xffffffffu, reserved);
     phantom = __reduce_add_sync(0xffffffffu, phantom);
@@ -299,8 +338,8 @@ __device__ __forceinline__ int next_owner(const int32_t *__restrict__ chunk_off,
 // One warp per contiguous span of chunks.  The count pass tests every candidate tile once and keeps the 32-bit
 // survival mask of each chunk (the first `mask_cap` chunks; later ones are simply re-tested), the emit pass expands
 // the stored masks into (tile, Gaussian) entries without repeating the geometry, skipping dead chunks outright.
-template <bool EMIT>
-__global__ void __launch_bounds__(256) cull_chunks_kernel(int n, int total_entries,
+template <bool EMIT, bool PER_SAMPLE>
+__global__ void __launch_bounds__(256, 8) cull_chunks_kernel(int n, int total_entries,
                                                           const PackedGaussian *__restrict__ rec,
                                                           const int4 *__restrict__ bbox,
                                                           const int32_t *__restrict__ chunk_off,
@@ -348,7 +387,7 @@ __global__ void __launch_bounds__(256) cull_chunks_kernel(int n, int total_entri
             int tx = 0, ty = 0;
             if (k < bb.w) {
                 tx = bb.x + k % bb.z; ty = bb.y + k / bb.z;
-                keep = known ? ((m >> lane) & 1u) != 0u : tile_survives(rec[g], tx, ty, c);
+                keep = known ? ((m >> lane) & 1u) != 0u : tile_survives<PER_SAMPLE>(rec[g], tx, ty, c);
             }
             if (!known) m = __ballot_sync(0xffffffffu, keep);
             if (!EMIT) {
@@ -632,6 +671,11 @@ static CullGeom make_cull_geom(unsigned H, unsigned W, unsigned bw, unsigned S, 
     c.S = (int)S; c.rs_time = rs; c.exposure = exposure;
     c.inv_H = 1.0f / (float)H;
     c.roll_eps = 4e-6f * fabsf(rs);
+    static const int per_sample = [] {
+        const char *e = getenv("B200_CULL_PER_SAMPLE");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    c.per_sample = per_sample;
     return c;
 }
 
@@ -681,8 +725,8 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     }
     B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, chunks, chunk_off, n, st));
     count_launch(2);
-    cull_chunks_kernel<false><<<CULL_GRID, 256, 0, st>>>(n, 0, rec, bbox, chunk_off, chunks, c, counters, masks, L.mask_cap,
-                                                         survivors, nullptr, nullptr, nullptr, nullptr);
+    (c.per_sample ? cull_chunks_kernel<false, true> : cull_chunks_kernel<false, false>)<<<CULL_GRID, 256, 0, st>>>(
+        n, 0, rec, bbox, chunk_off, chunks, c, counters, masks, L.mask_cap, survivors, nullptr, nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
     // (a later record of the shared join event by another caller is ordered after this one on the side stream)
     B200_CUDA(cudaStreamWaitEvent(st, side.join, 0));
@@ -727,9 +771,9 @@ extern "C" int b200_bin_cull_emit(int num_points, int num_entries, const void *p
     int32_t *ids_a = (int32_t *)(eb + E.ids_a);
     void *cub_ws = eb + E.cub;
     size_t cub_bytes = E.cub_bytes;
-    cull_chunks_kernel<true><<<CULL_GRID, 256, 0, st>>>(n, m, reinterpret_cast<const PackedGaussian *>(packed), bbox, chunk_off,
-                                                        chunks, c, counters, masks, G.mask_cap, nullptr, base_of, cursor,
-                                                        tkeys_a, ids_a);
+    (c.per_sample ? cull_chunks_kernel<true, true> : cull_chunks_kernel<true, false>)<<<CULL_GRID, 256, 0, st>>>(
+        n, m, reinterpret_cast<const PackedGaussian *>(packed), bbox, chunk_off, chunks, c, counters, masks, G.mask_cap, nullptr,
+        base_of, cursor, tkeys_a, ids_a);
     B200_LAUNCH_CHECK();
     int bits = key_end_bit(num_tiles) - 32;
     if (bits < 1) bits = 1;

@@ -311,6 +311,35 @@ def test_culled_binning_mask_cap_fallback():
         assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("cfg", [
+    ("c2", None, True, 5, 0.0, 1 / 60, None, None), ("c2", 60000, True, 10, 1 / 50, 1 / 60, 256, 320),
+    ("c4", 80000, True, 5, 1 / 50, 1 / 60, 480, 640), ("c3_rs", 100000, True, 1, 1 / 50, 0.0, 360, 640),
+    ("c1", None, False, 1, 0.0, 0.0, None, None)])
+def test_closed_form_tile_test_keeps_a_superset_of_the_per_sample_test(cfg, tmp_path):
+    """The binning's tile test covers the S blur samples with one interval test (binning.cu: may_touch_rect_closed_form).
+    It must keep every (tile, Gaussian) pair the sample-by-sample test keeps (B200_CULL_PER_SAMPLE=1, run in a separate
+    process because the switch is read once), in the same order, and at most a sliver more."""
+    import subprocess
+    import sys
+    import cull_dump
+    out = str(tmp_path / "per_sample.npz")
+    env = dict(os.environ, B200_CULL_PER_SAMPLE="1")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cull_dump.py"), out, repr(cfg)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ref = np.load(out)
+    total, ids, bins = cull_dump.culled_lists(*cfg)
+    assert total == int(ref["total"])
+    assert ids.size >= ref["ids"].size and ids.size <= 1.05 * ref["ids"].size + 64, (ids.size, ref["ids"].size)
+    rb, ri = ref["bins"], ref["ids"]
+    for t in range(bins.shape[0]):
+        mine, theirs = ids[bins[t, 0]:bins[t, 1]], ri[rb[t, 0]:rb[t, 1]]
+        if theirs.size == 0:
+            continue
+        it = iter(mine.tolist())
+        assert all(any(x == y for y in it) for x in theirs.tolist()), f"tile {t}: per-sample list is not a sub-list"
+
+
 def test_map_and_bins_golden_reference(golden):
     g = golden("map_bins.npz")
     H, W, bw = int(g["H"]), int(g["W"]), int(g["bw"])
