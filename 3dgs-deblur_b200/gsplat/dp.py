@@ -127,7 +127,7 @@ class ImageShardedTrainer:
     """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient exchange per step."""
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True,
-                 fused: bool = False, loss_fn=None):
+                 fused: bool = False, loss_fn=None, sh_chunks: int = 3):
         self.model, self.scene = model, scene
         if loss_fn is None:  # fused L1 (value + cotangent in one kernel); CUDA only, like the operators themselves
             from gsplat.losses import l1_loss as loss_fn
@@ -138,37 +138,47 @@ class ImageShardedTrainer:
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
         # The exchange is split where the backward pass splits: the SH coefficients are 48 of the 59 floats per Gaussian
-        # and their gradient is final as soon as the SH backward has run -- before the projection backward.  That slice
+        # and their gradient is final as soon as the SH backward has run -- before the projection backward.  That part
         # of the flat gradient buffer is reduced asynchronously from a post-accumulate hook, so most of the step's
         # exchange overlaps the rest of the backward pass; the remaining 11 floats per Gaussian (+ camera rows) follow
-        # when backward returns and overlap the Adam update of the SH block.  Two Adam instances = the same update as one
-        # (Adam is per-element), they only let the SH block step while the second exchange is still in flight.
+        # when backward returns.  Exchange and update are pipelined over contiguous CHUNKS of the flat buffers (the
+        # geometry block + `sh_chunks` pieces of the SH block): chunk i is updated by its own Adam instance as soon as
+        # its allreduce has landed, while the allreduce of chunk i+1 is still on the wire.  Adam is per-element and every
+        # instance sees the same step count and learning rate, so this is the same update as one optimizer over all
+        # parameters (a per-group learning rate would need chunk boundaries on parameter boundaries).
         fused_adam = model.flat.is_cuda
-        sh_params = [model.params["sh_dc"], model.params["sh_rest"]]
-        rest_params = [p for p in model.parameters() if all(p is not q for q in sh_params)]
-        if self.distributed:
-            self.opt_sh = torch.optim.Adam(sh_params, lr=lr, eps=1e-15, fused=fused_adam)
-            self.opt_rest = torch.optim.Adam(rest_params, lr=lr, eps=1e-15, fused=fused_adam)
-        else:  # nothing to overlap with: one multi-tensor launch
-            self.opt = torch.optim.Adam(rest_params + sh_params, lr=lr, eps=1e-15, fused=fused_adam)
         self.step_idx = 0
         # NCCL averages in the collective itself; gloo (CPU tests) only sums, so the 1/R scale is a separate pass there
         self._avg = self.distributed and dist.get_backend(group) == "nccl"
         self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
-        self._sh_work = None
+        self._sh_works = None
         self._sh_seen = 0
-        self._sh_slice = model.flat_grad[model.sh_start:]
-        self._rest_slice = model.flat_grad[:model.sh_start]
-        # the fused operator writes every gradient in one kernel: nothing is final early, nothing to overlap
+        if self.distributed:
+            total, lo = model.flat.numel(), model.sh_start
+            n_sh = max(1, int(sh_chunks))
+            cuts = [lo + (total - lo) * k // n_sh for k in range(n_sh + 1)]
+            bounds = [(0, lo)] + [(cuts[k], cuts[k + 1]) for k in range(n_sh) if cuts[k + 1] > cuts[k]]
+            self._chunks = []  # (gradient slice, Adam over an alias of the matching parameter slice)
+            for a, b_ in bounds:
+                alias = model.flat[a:b_].detach().requires_grad_(True)  # shares storage with the parameter views
+                alias.grad = model.flat_grad[a:b_]
+                self._chunks.append((alias.grad, torch.optim.Adam([alias], lr=lr, eps=1e-15, fused=fused_adam)))
+        else:  # nothing to overlap with: one multi-tensor launch over the parameter views
+            self.opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-15, fused=fused_adam)
+        # the fused operator writes every gradient in one kernel: nothing is final early, but the chunked
+        # exchange / update pipeline still applies
         self.overlap_sh = bool(overlap_sh and self.distributed and not self.fused)
         if self.overlap_sh:
             for name in ("sh_dc", "sh_rest"):
                 model.params[name].register_post_accumulate_grad_hook(self._on_sh_grad)
 
+    def _reduce_async(self, chunk_ids):
+        return [dist.all_reduce(self._chunks[i][0], op=self._op, group=self.group, async_op=True) for i in chunk_ids]
+
     def _on_sh_grad(self, _param):
         self._sh_seen += 1
         if self._sh_seen == 2:  # both halves of the cat() have landed in the flat buffer
-            self._sh_work = dist.all_reduce(self._sh_slice, op=self._op, group=self.group, async_op=True)
+            self._sh_works = self._reduce_async(range(1, len(self._chunks)))
 
     def image_index(self, step: int, n_images: int) -> int:
         return (step * self.world + self.rank) % n_images
@@ -185,20 +195,23 @@ class ImageShardedTrainer:
             m.zero_grad()
             rgb, alpha, xys, radii = render(m, cam, self.scene, cam_index)
         loss = self.loss_fn(rgb, target)
-        self._sh_seen, self._sh_work = 0, None
+        self._sh_seen, self._sh_works = 0, None
         loss.backward()
         if self.distributed:
             # gradients of the R images are averaged (each rank's loss is a per-image mean)
-            sh_work = self._sh_work or dist.all_reduce(self._sh_slice, op=self._op, group=self.group, async_op=True)
-            rest_work = dist.all_reduce(self._rest_slice, op=self._op, group=self.group, async_op=True)
-            sh_work.wait()
-            if not self._avg:
-                self._sh_slice.mul_(1.0 / self.world)
-            self.opt_sh.step()
-            rest_work.wait()
-            if not self._avg:
-                self._rest_slice.mul_(1.0 / self.world)
-            self.opt_rest.step()
+            n = len(self._chunks)
+            if self._sh_works is not None:  # SH chunks already on the wire (hook): geometry chunk goes last
+                order = list(range(1, n)) + [0]
+                works = self._sh_works + self._reduce_async([0])
+            else:
+                order = list(range(n))
+                works = self._reduce_async(order)
+            for i, w in zip(order, works):
+                g, opt = self._chunks[i]
+                w.wait()
+                if not self._avg:
+                    g.mul_(1.0 / self.world)
+                opt.step()
         else:
             self.opt.step()
         self.step_idx += 1
