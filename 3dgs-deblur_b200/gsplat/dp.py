@@ -127,7 +127,7 @@ class ImageShardedTrainer:
     """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient exchange per step."""
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True,
-                 fused: bool = False, loss_fn=None, sh_chunks: int = 3):
+                 fused: bool = False, loss_fn=None, sh_chunks: int = 3, optimizer: str = "b200"):
         self.model, self.scene = model, scene
         if loss_fn is None:  # fused L1 (value + cotangent in one kernel); CUDA only, like the operators themselves
             from gsplat.losses import l1_loss as loss_fn
@@ -142,10 +142,18 @@ class ImageShardedTrainer:
         # of the flat gradient buffer is reduced asynchronously from a post-accumulate hook, so most of the step's
         # exchange overlaps the rest of the backward pass; the remaining 11 floats per Gaussian (+ camera rows) follow
         # when backward returns.  Exchange and update are pipelined over contiguous CHUNKS of the flat buffers (the
-        # geometry block + `sh_chunks` pieces of the SH block): chunk i is updated by its own Adam instance as soon as
-        # its allreduce has landed, while the allreduce of chunk i+1 is still on the wire.  Adam is per-element and every
-        # instance sees the same step count and learning rate, so this is the same update as one optimizer over all
-        # parameters (a per-group learning rate would need chunk boundaries on parameter boundaries).
+        # geometry block + `sh_chunks` pieces of the SH block): chunk i is updated as soon as its allreduce has landed,
+        # while the allreduce of chunk i+1 is still on the wire.  Adam is per-element and every chunk sees the same step
+        # count and learning rate, so this is the same update as one optimizer over all parameters (a per-group
+        # learning rate would need chunk boundaries on parameter boundaries).
+        # optimizer = "b200": gsplat.optim.FlatAdam (one kernel per slice, clears the gradient slice in the same pass);
+        # "torch": torch.optim.Adam per chunk (what the CPU/gloo tests of this host logic inject).
+        if optimizer not in ("b200", "torch"):
+            raise ValueError("optimizer must be 'b200' or 'torch'")
+        self.flat_adam = None
+        if optimizer == "b200":
+            from gsplat.optim import FlatAdam
+            self.flat_adam = FlatAdam(model.flat, model.flat_grad, lr=lr, eps=1e-15)
         fused_adam = model.flat.is_cuda
         self.step_idx = 0
         # NCCL averages in the collective itself; gloo (CPU tests) only sums, so the 1/R scale is a separate pass there
@@ -158,12 +166,15 @@ class ImageShardedTrainer:
             n_sh = max(1, int(sh_chunks))
             cuts = [lo + (total - lo) * k // n_sh for k in range(n_sh + 1)]
             bounds = [(0, lo)] + [(cuts[k], cuts[k + 1]) for k in range(n_sh) if cuts[k + 1] > cuts[k]]
-            self._chunks = []  # (gradient slice, Adam over an alias of the matching parameter slice)
+            self._chunks = []  # (gradient slice, (begin, end) | torch Adam over an alias of the matching parameter slice)
             for a, b_ in bounds:
+                if self.flat_adam is not None:
+                    self._chunks.append((model.flat_grad[a:b_], (a, b_)))
+                    continue
                 alias = model.flat[a:b_].detach().requires_grad_(True)  # shares storage with the parameter views
                 alias.grad = model.flat_grad[a:b_]
                 self._chunks.append((alias.grad, torch.optim.Adam([alias], lr=lr, eps=1e-15, fused=fused_adam)))
-        else:  # nothing to overlap with: one multi-tensor launch over the parameter views
+        elif self.flat_adam is None:  # nothing to overlap with: one multi-tensor launch over the parameter views
             self.opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-15, fused=fused_adam)
         # the fused operator writes every gradient in one kernel: nothing is final early, but the chunked
         # exchange / update pipeline still applies
@@ -186,13 +197,15 @@ class ImageShardedTrainer:
     def train_step(self, cam: Dict, target: torch.Tensor, cam_index: int = 0):
         """fwd + L1 loss + bwd (+ gradient exchange) + Adam.  Returns the (device) loss tensor; no host sync."""
         m = self.model
+        clear = self.flat_adam is None  # FlatAdam leaves the gradient buffer zeroed behind it
         if self.fused:
-            if m.cam_vel is not None:
+            if clear and m.cam_vel is not None:
                 m.cam_vel.grad.zero_()  # the Gaussian rows are overwritten by the fused backward kernel
             rgb, alpha, info = render_fused(m, cam, self.scene, cam_index)
             xys, radii = None, info["radii"]
         else:
-            m.zero_grad()
+            if clear:
+                m.zero_grad()
             rgb, alpha, xys, radii = render(m, cam, self.scene, cam_index)
         loss = self.loss_fn(rgb, target)
         self._sh_seen, self._sh_works = 0, None
@@ -206,12 +219,19 @@ class ImageShardedTrainer:
             else:
                 order = list(range(n))
                 works = self._reduce_async(order)
+            if self.flat_adam is not None:
+                self.flat_adam.begin_step()
             for i, w in zip(order, works):
                 g, opt = self._chunks[i]
                 w.wait()
+                if self.flat_adam is not None:  # the 1/R of a summing backend is folded into the update
+                    self.flat_adam.update(opt[0], opt[1], 1.0 if self._avg else 1.0 / self.world, True)
+                    continue
                 if not self._avg:
                     g.mul_(1.0 / self.world)
                 opt.step()
+        elif self.flat_adam is not None:
+            self.flat_adam.step()
         else:
             self.opt.step()
         self.step_idx += 1

@@ -1,0 +1,47 @@
+"""Adam over the trainer's flat parameter buffer ("next" row f-2).
+
+The reference builds one `torch.optim.Adam(eps=1e-15)` per Splatfacto parameter group
+(nerfstudio/engine/optimizers.py:158-171, splatfacto.py:1063-1100).  `FlatAdam` keeps the two moment buffers flat, next
+to the flat parameter / gradient buffers of `gsplat.dp.FlatGaussians`, and updates any `[begin, end)` slice with one
+kernel (`b200_adam_step`): a data-parallel trainer can update slice i while the gradient exchange of slice i+1 is still
+in flight, the gradient slice is cleared in the same pass (no separate zero_grad fill), and a step costs one C call
+instead of a Python optimizer round trip per slice.  CUDA only."""
+import torch
+
+from . import _lib
+from ._lib import check, stream
+
+
+class FlatAdam:
+    def __init__(self, flat: torch.Tensor, flat_grad: torch.Tensor, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-15):
+        _lib.require_cuda(flat, flat_grad)
+        if flat.dtype != torch.float32 or flat_grad.dtype != torch.float32 or flat.shape != flat_grad.shape or flat.dim() != 1:
+            raise ValueError("FlatAdam: expected two 1-D float32 buffers of equal length")
+        self.flat, self.flat_grad = flat, flat_grad
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.step_count = 0
+        self._ptrs = (flat.data_ptr(), flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr())
+        self._lib = _lib.load()
+
+    def begin_step(self):
+        """Once per optimisation step, before the first `update` of that step."""
+        self.step_count += 1
+
+    def update(self, begin: int = 0, end: int = None, grad_scale: float = 1.0, zero_grad: bool = True):
+        """Adam update of flat[begin:end] from flat_grad[begin:end] on the current stream."""
+        end = self.flat.numel() if end is None else end
+        if not (0 <= begin <= end <= self.flat.numel()):
+            raise ValueError(f"FlatAdam.update: bad slice [{begin}, {end})")
+        off = 4 * begin
+        p, g, m, v = self._ptrs
+        with _lib.on_device(self.flat.device):
+            check(self._lib.b200_adam_step(end - begin, p + off, g + off, m + off, v + off, self.step_count, self.lr,
+                                           self.betas[0], self.betas[1], self.eps, float(grad_scale), 1 if zero_grad else 0,
+                                           stream()))
+
+    def step(self, zero_grad: bool = True):
+        """Whole-buffer update (single-GPU training)."""
+        self.begin_step()
+        self.update(0, None, 1.0, zero_grad)

@@ -480,15 +480,26 @@ def run_gpu_arm(args):
             on_path = [k for k in kernels if "note" not in kernels[k] or k == "bin_cull"]
             dom = max(on_path, key=lambda k: kernels[k]["ms"])
             walk = int(((bins[:, 1] - bins[:, 0]).long().sum().item()) * 256 * S)
-            traffic, traffic_src = None, None
-            tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full captures
+            traffic, traffic_src, issue = None, None, None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")  # per-launch figures from the committed ncu --set full captures
             if os.path.exists(tp) and args.n is None:
                 tj = json.load(open(tp)).get(args.config, {})
                 if dom in tj:
                     traffic, traffic_src = tj[dom]["dram_bytes"], tj[dom]["source"]
+                    if tj[dom].get("warp_instructions") and clocks and clocks.get("sm_mhz"):
+                        # the roofline that actually binds the blend: FP32 lanes x clock.  Instruction count
+                        # per launch from the ncu capture of this workload, duration measured live above.
+                        lane_instr = tj[dom]["warp_instructions"] * tj[dom]["active_lanes_per_instruction"]
+                        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                        peak_li = sms * 128 * clocks["sm_mhz"] * 1e6
+                        ach = lane_instr / (kernels[dom]["ms"] * 1e-3)
+                        issue = {"bound": "fp32-lane issue", "lane_instructions_per_launch": int(lane_instr), "achieved": ach,
+                                 "peak": peak_li, "unit": "lane-instr/s", "frac": round(ach / peak_li, 4),
+                                 "peak_source": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock sampled during the timed region)" % (
+                                     sms, clocks["sm_mhz"])}
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                         "frac": round(kernels[dom]["gbs"] / peak, 5), "traffic": traffic, "traffic_source": traffic_src,
-                        "peak_source": peak_src,
+                        "peak_source": peak_src, "issue": issue,
                         "note": ("blend kernels are FP32-issue/MUFU/SHFL/atomic bound, not HBM bound (SURVEY 0.5): "
                                  "pixel-Gaussian-sample evaluations upper bound per launch = %d -> %.3g eval/s" % (
                                      walk, walk / (kernels[dom]["ms"] * 1e-3))),

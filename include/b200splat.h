@@ -270,6 +270,17 @@ B200_API size_t b200_l1_loss_ws_bytes(void);
 B200_API int b200_l1_loss(long long numel, const float *pred, const float *target, float *loss, float *grad, void *ws,
                           int ws_is_zeroed, void *stream);
 
+/* ---- optimizer ("next" row f-2 of SURVEY section 8) ---------------------------------------------
+ * One Adam update (no weight decay, no amsgrad: what nerfstudio/engine/optimizers.py:158-171 builds for every Splatfacto
+ * group, eps = 1e-15) of `numel` consecutive floats of the flat {param, grad, exp_avg, exp_avg_sq} buffers:
+ *   g' = grad_scale * grad;  m += (1 - beta1)(g' - m);  v = beta2 v + (1 - beta2) g'^2;
+ *   param -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps);   grad = 0 if zero_grad.
+ * `step` counts from 1.  The four pointers may point anywhere into equally aligned buffers (same offset each), so a
+ * trainer can update slice by slice as gradient exchanges complete. */
+B200_API int b200_adam_step(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq, int step,
+                            float lr, float beta1, float beta2, float eps, float grad_scale, int zero_grad,
+                            void *stream);
+
 #ifdef __cplusplus
 }
 #endif

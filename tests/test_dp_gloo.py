@@ -50,7 +50,7 @@ def _worker(rank, world, port, out):
     # parameter views alias the flat buffer, gradient views alias the flat gradient buffer
     model.params["means"].data[0, 0] = 7.0
     assert model.flat[0] == 7.0
-    tr = dp.ImageShardedTrainer(model, scene, lr=1e-2, loss_fn=_torch_l1)
+    tr = dp.ImageShardedTrainer(model, scene, lr=1e-2, loss_fn=_torch_l1, optimizer="torch")
     assert [tr.image_index(s, 4) for s in range(3)] == [(s * world + rank) % 4 for s in range(3)]
     cams = [dict(w=float(i + 1)) for i in range(4)]
     for step in range(3):
@@ -63,7 +63,7 @@ def _worker(rank, world, port, out):
     # the overlapped exchange (SH slice reduced from the autograd hook) gives the same parameters as the plain one
     model2 = dp.FlatGaussians(scene, "cpu", n_cameras=4, optimize_velocities=True)
     model2.params["means"].data[0, 0] = 7.0  # same aliasing probe as the first model
-    tr2 = dp.ImageShardedTrainer(model2, scene, lr=1e-2, overlap_sh=False, loss_fn=_torch_l1)
+    tr2 = dp.ImageShardedTrainer(model2, scene, lr=1e-2, overlap_sh=False, loss_fn=_torch_l1, optimizer="torch")
     assert tr.overlap_sh and not tr2.overlap_sh
     for step in range(3):
         i = tr2.image_index(step, 4)
@@ -101,7 +101,7 @@ def test_single_process_trainer_matches_manual_adam():
     scene = synthetic.make_scene("c1", n_override=20)
     model = dp.FlatGaussians(scene, "cpu")
     ref = model.flat.detach().clone()
-    tr = dp.ImageShardedTrainer(model, scene, lr=1e-2, loss_fn=_torch_l1)
+    tr = dp.ImageShardedTrainer(model, scene, lr=1e-2, loss_fn=_torch_l1, optimizer="torch")
     loss = tr.train_step(dict(w=1.0), torch.zeros(scene["H"], scene["W"], 3))
     assert torch.isfinite(loss)
     # first Adam step moves every parameter with a non-zero gradient by lr (bias-corrected), opposite to its sign
