@@ -110,9 +110,13 @@ def run_cpu_arm(args, one_shot=False):
     the blend forward + backward on a centred band of image rows (time scaled by H / band) and, when even the
     per-Gaussian stages (projection, SH, binning; ~0.4 s) exceed the per-step budget, those stages are timed every m-th
     step and their last measured time is charged to the steps in between.  The sample is stated in the JSON."""
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = int(os.environ.get("B200_CPU_THREADS", os.cpu_count() or 1))
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently make this a 1-thread
+    # baseline; the oracle's OpenMP runtime reads the variable when liboracle.so is loaded (below), so override it here
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     step, d = cpu_step_factory(args.config, args.n)
+    from oracle import oracle as _O
+    cores = _O.set_threads(cores)  # the count the OpenMP runtime actually uses
     H = d["H"]
     n_steps = 1 if one_shot else args.steps + args.warmup
     budget = float(os.environ.get("B200_CPU_ARM_BUDGET_S", "10" if one_shot else "150")) / max(n_steps, 1)

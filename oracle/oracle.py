@@ -29,6 +29,13 @@ def lib():
     return _LIB
 
 
+def set_threads(n=0):
+    """Set (n > 0) and return the OpenMP thread count of the C oracle."""
+    fn = lib().orc_set_threads
+    fn.restype, fn.argtypes = C.c_int, [C.c_int]
+    return int(fn(int(n)))
+
+
 def _f(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -39,7 +39,22 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #define ORC_MAX_BLUR 10 /* helpers.cuh:222 */
+
+/* thread control for the timed CPU baseline (bench.py): launchers such as torchrun export OMP_NUM_THREADS=1 */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 /* ------------------------------------------------------------------ helpers */
 
