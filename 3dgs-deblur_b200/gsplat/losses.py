@@ -54,3 +54,89 @@ class _L1Loss(Function):
 def l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """mean |pred - target| as a 0-d tensor; differentiable w.r.t. `pred` only."""
     return _L1Loss.apply(pred, target)
+
+
+# ---- SSIM and the full photometric loss (splatfacto.py:957-975) -------------------------------------------------
+
+_ssim_ws = {}
+
+
+def _ssim_workspace(dev, H, W, C):
+    key = (dev.index, stream(), H, W, C)
+    ws = _ssim_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.load().b200_ssim_ws_bytes(H, W, C), dtype=torch.uint8, device=dev)
+        _ssim_ws[key] = ws
+    return ws
+
+
+def _check_images(name, pred, target):
+    _lib.require_cuda(pred, target)
+    if pred.shape != target.shape or pred.dim() != 3:
+        raise ValueError(f"{name}: expected two (H, W, C) images of equal shape, got {tuple(pred.shape)} / {tuple(target.shape)}")
+    if pred.dtype != torch.float32 or target.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32 tensors")
+    if pred.shape[0] < 11 or pred.shape[1] < 11:
+        raise ValueError(f"{name}: SSIM needs an image of at least 11 x 11 pixels")
+
+
+class _Photometric(Function):
+    """(1 - lam) * L1 + lam * (1 - SSIM) in three kernels (L1, SSIM forward, SSIM backward + combine); lam = None
+    returns the plain SSIM value instead."""
+
+    @staticmethod
+    def forward(ctx, pred, target, lam):
+        _check_images("photometric_loss" if lam is not None else "ssim", pred, target)
+        pred_c, target_c = pred.contiguous(), target.contiguous()
+        H, W, C = pred_c.shape
+        dev, lib = pred.device, _lib.load()
+        need = ctx.needs_input_grad[0]
+        with _lib.on_device(dev):
+            f32 = dict(dtype=torch.float32, device=dev)
+            out = torch.empty((), **f32)
+            ssim_val = torch.empty((), **f32)
+            maps = torch.empty(lib.b200_ssim_maps_bytes(H, W, C) // 4, **f32) if need else None
+            l1, g1 = None, None
+            if lam is not None:
+                l1 = torch.empty((), **f32)
+                g1 = torch.empty_like(pred_c) if need else None
+                check(lib.b200_l1_loss(pred_c.numel(), ptr(pred_c), ptr(target_c), ptr(l1), ptr(g1), ptr(_workspace(dev)), 1,
+                                       stream()))
+            check(lib.b200_ssim_forward(H, W, C, ptr(pred_c), ptr(target_c), ptr(maps), ptr(ssim_val),
+                                        ptr(out) if lam is not None else None, ptr(l1), float(lam or 0.0),
+                                        ptr(_ssim_workspace(dev, H, W, C)), 1, stream()))
+        ctx.save_for_backward(pred_c, target_c)
+        ctx.maps, ctx.g1, ctx.lam = maps, g1, lam
+        ctx.ssim_value = ssim_val
+        return out if lam is not None else ssim_val
+
+    @staticmethod
+    def backward(ctx, v):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("photometric_loss / ssim: the target image is a constant (no gradient)")
+        pred_c, target_c = ctx.saved_tensors
+        H, W, C = pred_c.shape
+        lam = ctx.lam
+        with _lib.on_device(pred_c.device):
+            grad = ctx.g1 if ctx.g1 is not None else torch.empty_like(pred_c)  # the L1 cotangent is combined in place
+            v = v.contiguous().float()
+            if lam is None:   # d SSIM / d pred
+                scale, add_in, add_scale = 1.0, None, 0.0
+            else:             # (1 - lam) * sign / n - lam * d SSIM / d pred
+                scale, add_in, add_scale = -float(lam), ctx.g1, 1.0 - float(lam)
+            check(_lib.load().b200_ssim_backward(H, W, C, ptr(pred_c), ptr(target_c), ptr(ctx.maps), scale, ptr(add_in),
+                                                 add_scale, ptr(v), ptr(grad), stream()))
+        ctx.maps = ctx.g1 = None
+        return grad, None, None
+
+
+def ssim(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """pytorch_msssim.SSIM(data_range=1, size_average=True, channel=C) of two (H, W, C) images (splatfacto.py:260,958);
+    differentiable w.r.t. `pred`."""
+    return _Photometric.apply(pred, target, None)
+
+
+def photometric_loss(pred: torch.Tensor, target: torch.Tensor, ssim_lambda: float = 0.2) -> torch.Tensor:
+    """Splatfacto's main loss (splatfacto.py:957-975): (1 - ssim_lambda) * mean|target - pred| + ssim_lambda *
+    (1 - SSIM(target, pred)); differentiable w.r.t. `pred`."""
+    return _Photometric.apply(pred, target, float(ssim_lambda))

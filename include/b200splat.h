@@ -270,6 +270,23 @@ B200_API size_t b200_l1_loss_ws_bytes(void);
 B200_API int b200_l1_loss(long long numel, const float *pred, const float *target, float *loss, float *grad, void *ws,
                           int ws_is_zeroed, void *stream);
 
+/* SSIM term of the photometric loss, (1 - lambda) * L1 + lambda * (1 - SSIM) (nerfstudio/models/splatfacto.py:957-975;
+ * SSIM = pytorch_msssim.SSIM(data_range=1, size_average=True, channel=C): 11-tap Gaussian window sigma 1.5, separable,
+ * valid padding, K = (0.01, 0.03), mean over channels and the (H-10) x (W-10) valid positions).  Images are (H, W, C).
+ *   b200_ssim_forward: ssim_out[0] = mean SSIM; if loss_out: loss_out[0] = (1 - lambda) * l1_loss[0] + lambda * (1 - SSIM)
+ *       (l1_loss null = 0); if maps (b200_ssim_maps_bytes bytes): the three partial-derivative maps for the backward.
+ *   b200_ssim_backward: grad = [v_scale[0] *] (add_scale * add_in + scale * dSSIM/dpred); add_in, v_scale optional.
+ *       With add_in = the L1 cotangent, add_scale = 1 - lambda, scale = -lambda this is the photometric cotangent.
+ * ws: b200_ssim_ws_bytes bytes, 16-byte aligned, ws_is_zeroed as for b200_l1_loss.  Deterministic. */
+B200_API size_t b200_ssim_ws_bytes(unsigned img_height, unsigned img_width, unsigned channels);
+B200_API size_t b200_ssim_maps_bytes(unsigned img_height, unsigned img_width, unsigned channels);
+B200_API int b200_ssim_forward(unsigned img_height, unsigned img_width, unsigned channels, const float *pred,
+                               const float *target, float *maps, float *ssim_out, float *loss_out, const float *l1_loss,
+                               float ssim_lambda, void *ws, int ws_is_zeroed, void *stream);
+B200_API int b200_ssim_backward(unsigned img_height, unsigned img_width, unsigned channels, const float *pred,
+                                const float *target, const float *maps, float scale, const float *add_in,
+                                float add_scale, const float *v_scale, float *grad, void *stream);
+
 /* ---- optimizer ("next" row f-2 of SURVEY section 8) ---------------------------------------------
  * One Adam update (no weight decay, no amsgrad: what nerfstudio/engine/optimizers.py:158-171 builds for every Splatfacto
  * group, eps = 1e-15) of `numel` consecutive floats of the flat {param, grad, exp_avg, exp_avg_sq} buffers:

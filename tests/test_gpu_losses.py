@@ -1,0 +1,68 @@
+"""GPU parity of the fused loss kernels against the CPU oracles: L1 vs torch, SSIM / photometric loss vs
+oracle/ssim_oracle.py (fp64 autograd restatement of pytorch_msssim; parity of that restatement is unpinned, see its
+header).  Tolerances: values 2e-6 relative + 1e-6 absolute (fp32 filtering of 121 taps vs fp64); cotangents 1e-5 of the
+tensor's max magnitude + 1e-4 relative."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ssim_oracle as SO
+
+if torch.cuda.is_available():
+    from gsplat.losses import l1_loss, photometric_loss, ssim
+
+
+def _pair(H, W, C, seed, smooth=True):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.rand(H, W, C, generator=g)
+    if smooth:  # image-like content: low-pass noise, so local variances are small and SSIM is far from 0
+        k = torch.ones(C, 1, 5, 5) / 25
+        t = torch.nn.functional.conv2d(t.permute(2, 0, 1)[None], k, padding=2, groups=C)[0].permute(1, 2, 0).contiguous()
+    p = (t + 0.1 * torch.randn(H, W, C, generator=g)).clamp(0, 1).contiguous()
+    return p, t
+
+
+@pytest.mark.parametrize("H,W,C,smooth", [(800, 800, 3, True), (37, 53, 3, True), (11, 11, 3, False), (64, 27, 1, True),
+                                          (48, 48, 4, False), (16, 200, 3, True)])
+def test_ssim_and_photometric_loss_vs_oracle(H, W, C, smooth):
+    p, t = _pair(H, W, C, seed=H * 1000 + W + C, smooth=smooth)
+    p64 = p.double().requires_grad_(True)
+    ref_ssim = SO.ssim_hwc(p64, t.double())
+    (g_ssim,) = torch.autograd.grad(ref_ssim, p64)
+    ref_loss = SO.photometric_loss(p64, t.double(), 0.2)
+    (g_loss,) = torch.autograd.grad(ref_loss * 1.7, p64)
+
+    pc = p.cuda().requires_grad_(True)
+    tc = t.cuda()
+    out = ssim(pc, tc)
+    (g,) = torch.autograd.grad(out, pc)
+    assert abs(float(out) - float(ref_ssim)) <= 2e-6 * abs(float(ref_ssim)) + 1e-6
+    tol = 1e-5 * float(g_ssim.abs().max())
+    torch.testing.assert_close(g.cpu().double(), g_ssim, rtol=1e-4, atol=tol)
+
+    loss = photometric_loss(pc, tc, 0.2)
+    (gl,) = torch.autograd.grad(loss * 1.7, pc)
+    assert abs(float(loss) - float(ref_loss)) <= 2e-6 * abs(float(ref_loss)) + 1e-6
+    # the L1 part of the cotangent is +-1/n exactly; at |p - t| ~ 0 fp32 and fp64 may pick different signs: none here
+    torch.testing.assert_close(gl.cpu().double(), g_loss, rtol=1e-4, atol=1e-5 * float(g_loss.abs().max()))
+    # deterministic
+    assert torch.equal(ssim(pc, tc), out) and torch.equal(photometric_loss(pc, tc, 0.2), loss)
+    # lambda = 0 is the plain L1, lambda = 1 is 1 - SSIM
+    torch.testing.assert_close(photometric_loss(pc, tc, 0.0), l1_loss(pc, tc), rtol=1e-6, atol=0)
+    torch.testing.assert_close(photometric_loss(pc, tc, 1.0), 1 - out, rtol=1e-6, atol=1e-7)
+
+
+def test_ssim_identities_and_errors():
+    p, t = _pair(40, 56, 3, seed=1)
+    pc, tc = p.cuda(), t.cuda()
+    assert abs(float(ssim(tc, tc)) - 1.0) < 1e-6  # SSIM(x, x) = 1
+    assert abs(float(ssim(pc, tc)) - float(ssim(tc, pc))) < 1e-6  # symmetric
+    with pytest.raises(ValueError):
+        ssim(pc[:10], tc[:10])  # shorter than the 11-tap window
+    with pytest.raises(ValueError):
+        ssim(pc, tc[:, :50])
+    with pytest.raises(RuntimeError):
+        ssim(p, t)  # CPU tensors: no CPU path
+    with pytest.raises(RuntimeError):
+        photometric_loss(pc.double(), tc.double())
