@@ -9,15 +9,15 @@
 
 namespace b200 {
 
-struct AdamArgs {
-    float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale;
+struct AdamArgs {  // every derived constant is formed in double on the host, like the Python optimizer does
+    float lr_over_bc1, inv_sqrt_bc2, one_minus_beta1, beta2, one_minus_beta2, eps, grad_scale;
     int zero_grad;
 };
 
 __device__ __forceinline__ void adam_one(float &p, float &g, float &m, float &v, const AdamArgs &a) {
     const float gs = g * a.grad_scale;
-    m = m + (1.0f - a.beta1) * (gs - m);                  // exp_avg.lerp_(grad, 1 - beta1)
-    v = a.beta2 * v + (1.0f - a.beta2) * gs * gs;         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m = m + a.one_minus_beta1 * (gs - m);                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = a.beta2 * v + a.one_minus_beta2 * (gs * gs);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(v) * a.inv_sqrt_bc2 + a.eps;
     p = p - a.lr_over_bc1 * (m / denom);
     if (a.zero_grad) g = 0.f;
@@ -27,6 +27,8 @@ constexpr int ADAM_THREADS = 256;
 
 __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(long long n, float *__restrict__ p, float *__restrict__ g,
                                                             float *__restrict__ m, float *__restrict__ v, AdamArgs a) {
+    // one 16-byte vector per thread, many short CTAs: a collective kernel of the next gradient slice (NCCL) can take
+    // SMs as they free up instead of waiting behind persistent grid-stride CTAs
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     float4 *p4 = reinterpret_cast<float4 *>(p), *g4 = reinterpret_cast<float4 *>(g);
@@ -54,22 +56,23 @@ __global__ void adam_head_kernel(int n, float *p, float *g, float *m, float *v, 
 using namespace b200;
 
 extern "C" int b200_adam_step(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq, int step,
-                              float lr, float beta1, float beta2, float eps, float grad_scale, int zero_grad,
+                              double lr, double beta1, double beta2, double eps, double grad_scale, int zero_grad,
                               void *stream) {
     B200_REQUIRE(numel >= 0, "numel must be >= 0");
     if (numel == 0) return B200_OK;
     B200_REQUIRE(param && grad && exp_avg && exp_avg_sq, "null pointer");
     B200_REQUIRE(step >= 1, "step counts from 1");
-    B200_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "betas must lie in [0, 1)");
+    B200_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0, "betas must lie in [0, 1)");
     const uintptr_t mis = reinterpret_cast<uintptr_t>(param) & 15u;
     B200_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15u) == mis && (reinterpret_cast<uintptr_t>(exp_avg) & 15u) == mis &&
                      (reinterpret_cast<uintptr_t>(exp_avg_sq) & 15u) == mis && (mis & 3u) == 0,
                  "the four buffers must share their alignment modulo 16 bytes (same offset into equally aligned flat buffers)");
     AdamArgs a;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    a.lr_over_bc1 = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    a.lr_over_bc1 = (float)(lr / bc1);
     a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale; a.zero_grad = zero_grad ? 1 : 0;
+    a.one_minus_beta1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.one_minus_beta2 = (float)(1.0 - beta2);
+    a.eps = (float)eps; a.grad_scale = (float)grad_scale; a.zero_grad = zero_grad ? 1 : 0;
     cudaStream_t st = as_stream(stream);
     long long head = mis ? (long long)((16u - mis) >> 2) : 0;
     if (head > numel) head = numel;
@@ -81,7 +84,7 @@ extern "C" int b200_adam_step(long long numel, float *param, float *grad, float 
     }
     const long long n4 = numel >> 2;
     long long want = (n4 + ADAM_THREADS - 1) / ADAM_THREADS;
-    const long long cap = 148ll * 16;  // 16 CTAs of 256 threads per SM, grid-stride beyond that
+    const long long cap = 1ll << 30;
     const int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     adam_kernel<<<blocks, ADAM_THREADS, 0, st>>>(numel, param, grad, exp_avg, exp_avg_sq, a);
     B200_LAUNCH_CHECK();

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200splat.so")
 
-_p, _i, _u, _f, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_size_t
+_p, _i, _u, _f, _d, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); mirrors include/b200splat.h one to one
 SIGNATURES = {
@@ -50,7 +50,7 @@ SIGNATURES = {
     "b200_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _p, _p]),
-    "b200_adam_step": (_i, [C.c_longlong, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _i, _p]),
+    "b200_adam_step": (_i, [C.c_longlong, _p, _p, _p, _p, _i, _d, _d, _d, _d, _d, _i, _p]),
     "b200_ssim_ws_bytes": (_sz, [_u, _u, _u]),
     "b200_ssim_maps_bytes": (_sz, [_u, _u, _u]),
     "b200_ssim_forward": (_i, [_u, _u, _u, _p, _p, _p, _p, _p, _p, _f, _p, _i, _p]),

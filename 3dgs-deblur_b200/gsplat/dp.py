@@ -127,7 +127,7 @@ class ImageShardedTrainer:
     """One process per GPU; rank r renders image (step * world + r) % n_images; one gradient exchange per step."""
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, overlap_sh: bool = True,
-                 fused: bool = False, loss_fn=None, sh_chunks: int = 3, optimizer: str = "b200"):
+                 fused: bool = False, loss_fn=None, sh_chunks: int = 1, optimizer: str = "b200"):
         self.model, self.scene = model, scene
         if loss_fn is None:  # fused L1 (value + cotangent in one kernel); CUDA only, like the operators themselves
             from gsplat.losses import l1_loss as loss_fn
@@ -145,7 +145,9 @@ class ImageShardedTrainer:
         # geometry block + `sh_chunks` pieces of the SH block): chunk i is updated as soon as its allreduce has landed,
         # while the allreduce of chunk i+1 is still on the wire.  Adam is per-element and every chunk sees the same step
         # count and learning rate, so this is the same update as one optimizer over all parameters (a per-group
-        # learning rate would need chunk boundaries on parameter boundaries).
+        # learning rate would need chunk boundaries on parameter boundaries).  Measured at 2 GPUs: every extra collective
+        # costs more fixed latency on the NCCL stream than its pipelining hides (969 / 910 images/s with 1 / 3 SH
+        # chunks), hence the default of one SH chunk + the geometry chunk.
         # optimizer = "b200": gsplat.optim.FlatAdam (one kernel per slice, clears the gradient slice in the same pass);
         # "torch": torch.optim.Adam per chunk (what the CPU/gloo tests of this host logic inject).
         if optimizer not in ("b200", "torch"):

@@ -292,10 +292,11 @@ B200_API int b200_ssim_backward(unsigned img_height, unsigned img_width, unsigne
  * group, eps = 1e-15) of `numel` consecutive floats of the flat {param, grad, exp_avg, exp_avg_sq} buffers:
  *   g' = grad_scale * grad;  m += (1 - beta1)(g' - m);  v = beta2 v + (1 - beta2) g'^2;
  *   param -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps);   grad = 0 if zero_grad.
- * `step` counts from 1.  The four pointers may point anywhere into equally aligned buffers (same offset each), so a
+ * `step` counts from 1; the hyper-parameters are doubles so that 1 - beta, the bias corrections and lr / (1 - beta1^step)
+ * are formed in double exactly like the Python optimizer forms them.  The four pointers may point anywhere into equally aligned buffers (same offset each), so a
  * trainer can update slice by slice as gradient exchanges complete. */
 B200_API int b200_adam_step(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq, int step,
-                            float lr, float beta1, float beta2, float eps, float grad_scale, int zero_grad,
+                            double lr, double beta1, double beta2, double eps, double grad_scale, int zero_grad,
                             void *stream);
 
 #ifdef __cplusplus
