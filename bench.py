@@ -338,41 +338,27 @@ def run_gpu_arm(args):
     cam_host = [torch.cat([c["viewmat"].reshape(-1), c["lin_vel"], c["ang_vel"], c["cam_pos"]]).pin_memory() for c in my]
     e2e_steps = max(5, args.steps // 2)
 
-    # double-buffered prefetch on a copy stream (what a datamanager does: pinned uint8 image + camera floats), the
-    # loss of step k-1 is read back while step k is already queued; every step's inputs cross PCIe inside the timed
-    # region and every step's loss is read.
-    copy_stream = torch.cuda.Stream(device=dev)
-    buf_img = [torch.empty((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
-    buf_cam = [torch.empty(21, dtype=torch.float32, device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    main_stream = torch.cuda.current_stream()
+    # double-buffered prefetch on a copy stream (gsplat.data.ImagePrefetcher: what a datamanager does -- pinned uint8
+    # image + camera floats), the loss of step k-1 is read back while step k is already queued; every step's inputs cross
+    # PCIe inside the timed region and every step's loss is read.
+    from gsplat.data import ImagePrefetcher
 
-    def prefetch(k):
-        b, i = k % 2, k % n_img
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])
-            buf_img[b].copy_(targets_u8[i], non_blocking=True)
-            buf_cam[b].copy_(cam_host[i], non_blocking=True)
-            ready[b].record(copy_stream)
+    prefetcher = ImagePrefetcher(targets_u8, cam_host, dev)
+    main_stream = torch.cuda.current_stream()
 
     loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_done = [torch.cuda.Event() for _ in range(2)]
 
     def e2e_loop(n_steps):
         losses = []
-        for b in range(2):
-            consumed[b].record(main_stream)
-        prefetch(0)
+        prefetcher.start(0)
         for k in range(n_steps):
             b, i = k % 2, k % n_img
-            main_stream.wait_event(ready[b])
-            prefetch(k + 1)
-            tgt = buf_img[b].float() / 255
-            ch = buf_cam[b]
+            img_u8, ch = prefetcher.get(next_index=(k + 1) % n_img)
+            tgt = img_u8.float() / 255
             cam = dict(cams[i], viewmat=ch[:12].view(3, 4), lin_vel=ch[12:15], ang_vel=ch[15:18], vel0=ch[12:18], cam_pos=ch[18:21])
             loss = trainer.train_step(cam, tgt, i)
-            consumed[b].record(main_stream)
+            prefetcher.done()
             loss_host[b].copy_(loss.detach().reshape(1), non_blocking=True)  # loss D2H (4 bytes) every step
             loss_done[b].record(main_stream)
             if k > 0:  # read the previous step's loss: it completed before this step's intersect-count sync
@@ -393,7 +379,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    h2d = H * W * 3 + 21 * 4
+    h2d = prefetcher.bytes_per_step
     e2e = {"value": world * 1000.0 / e2e_ms, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4 + 8, "steps": e2e_steps,
            "path": "gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians via gsplat.dp.ImageShardedTrainer"}

@@ -35,7 +35,7 @@ def ssim_hwc(pred, target, data_range=1.0, K=(0.01, 0.03)):
     """Mean SSIM of two (H, W, C) images, as SSIM(data_range, size_average=True, channel=C)(X[None], Y[None])."""
     X = target.permute(2, 0, 1)[None]
     Y = pred.permute(2, 0, 1)[None]
-    win = gauss_window(dtype=X.dtype)
+    win = gauss_window(dtype=torch.float32).to(X.dtype)  # the library builds the window in float32, then casts it
     C1, C2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
     mu1, mu2 = gaussian_filter(X, win), gaussian_filter(Y, win)
     mu1_sq, mu2_sq, mu1_mu2 = mu1 * mu1, mu2 * mu2, mu1 * mu2

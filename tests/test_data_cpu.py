@@ -1,0 +1,87 @@
+"""CPU: gsplat.data.load_transforms against the reference's own dataparser (fixtures from tests/golden/make_golden_data.py:
+nerfstudio_dataparser.py run on fabricated datasets), and the camera conversion of Splatfacto.get_outputs."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3dgs-deblur_b200"))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _materialise(tmp_path, meta):
+    """Write the fabricated dataset the fixture was parsed from (blank images: only their size is ever read)."""
+    from PIL import Image
+    for sub in ("images", "images_2"):
+        os.makedirs(tmp_path / sub)
+        for fr in meta["frames"]:
+            Image.fromarray(np.zeros((240, 320, 3), np.uint8)).save(tmp_path / sub / os.path.basename(fr["file_path"]))
+    json.dump(meta, open(tmp_path / "transforms.json", "w"))
+
+
+@pytest.mark.parametrize("case", ["data_case1", "data_case2", "data_case3"])
+def test_load_transforms_matches_reference_dataparser(case, tmp_path):
+    from gsplat.data import load_transforms
+    spec = json.load(open(os.path.join(GOLD, case + ".json")))
+    gold = np.load(os.path.join(GOLD, case + ".npz"))
+    _materialise(tmp_path, spec["meta"])
+    for split in ("train", "val"):
+        out = load_transforms(str(tmp_path), split=split, **spec["config"])
+        pre = split + "_"
+        assert [os.path.relpath(p, str(tmp_path)) for p in out["image_filenames"]] == list(gold[pre + "image_filenames"])
+        np.testing.assert_allclose(out["camera_to_worlds"], gold[pre + "camera_to_worlds"], rtol=0, atol=2e-6)
+        for k in ("fx", "fy", "cx", "cy"):
+            np.testing.assert_allclose(out[k], gold[pre + k], rtol=1e-6)
+        assert np.array_equal(out["height"], gold[pre + "height"]) and np.array_equal(out["width"], gold[pre + "width"])
+        if pre + "velocities" in gold:
+            np.testing.assert_allclose(out["velocities"], gold[pre + "velocities"], rtol=2e-6, atol=1e-7)
+            assert out["exposure_time"] == pytest.approx(float(gold[pre + "exposure_time"]))
+            assert out["rolling_shutter_time"] == pytest.approx(float(gold[pre + "rolling_shutter_time"]))
+        else:
+            assert out["velocities"] is None and out["exposure_time"] is None
+        assert out["dataparser_scale"] == pytest.approx(float(gold[pre + "dataparser_scale"]), rel=1e-6)
+        np.testing.assert_allclose(out["dataparser_transform"], gold[pre + "dataparser_transform"], rtol=0, atol=2e-6)
+
+
+def test_load_transforms_errors(tmp_path):
+    from gsplat.data import load_transforms
+    spec = json.load(open(os.path.join(GOLD, "data_case1.json")))
+    meta = spec["meta"]
+    _materialise(tmp_path, meta)
+    with pytest.raises(ValueError):
+        load_transforms(str(tmp_path), split="nope", downscale_factor=1)
+    with pytest.raises(ValueError):
+        load_transforms(str(tmp_path), orientation_method="pca")
+    del meta["frames"][3]["camera_angular_velocity"]
+    json.dump(meta, open(tmp_path / "transforms.json", "w"))
+    with pytest.raises(AssertionError):
+        load_transforms(str(tmp_path))
+
+
+def test_to_gsplat_camera_is_the_splatfacto_camera_block():
+    """splatfacto.py:733-747,799-800: flip y/z of the camera axes, invert analytically, rotate the velocities by the flip."""
+    from gsplat.data import to_gsplat_camera
+    g = torch.Generator().manual_seed(0)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    if torch.det(q) < 0:
+        q[:, 2] = -q[:, 2]
+    t = torch.randn(3, generator=g)
+    c2w = torch.cat([q, t[:, None]], dim=1)
+    vel = torch.randn(6, generator=g)
+    cam = to_gsplat_camera(c2w, vel)
+    R_edit = torch.diag(torch.tensor([1.0, -1.0, -1.0]))
+    c2w_gs = torch.eye(4)
+    c2w_gs[:3, :3] = q @ R_edit
+    c2w_gs[:3, 3] = t
+    torch.testing.assert_close(cam["viewmat"], torch.linalg.inv(c2w_gs), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(cam["viewmat"][:3, :3] @ t + cam["viewmat"][:3, 3], torch.zeros(3), rtol=0, atol=1e-6)
+    torch.testing.assert_close(cam["lin_vel"], R_edit @ vel[:3])
+    torch.testing.assert_close(cam["ang_vel"], R_edit @ vel[3:])
+    torch.testing.assert_close(cam["cam_pos"], t)
+    with pytest.raises(RuntimeError):
+        from gsplat.data import ImagePrefetcher
+        ImagePrefetcher([torch.zeros(4, 4, 3, dtype=torch.uint8)], [torch.zeros(21)], "cpu")
