@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--images", type=int, default=8, help="distinct training images per rank")
     ap.add_argument("--profile", action="store_true", help="also report the summed device time of all kernels per step (CUPTI)")
+    ap.add_argument("--loss", default="l1", choices=["l1", "photometric"],
+                    help="l1 = BASELINE's loss; photometric = Splatfacto's 0.8 L1 + 0.2 (1 - SSIM) through the fused kernels")
     ap.add_argument("--sh-chunks", type=int, default=1, help="pieces of the SH block in the gradient exchange (N > 1)")
     ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"], help="FlatAdam kernel or torch's fused Adam")
     ap.add_argument("--no-fused-path", action="store_true", help="skip the extra fused-operator measurement")
@@ -249,7 +251,11 @@ def run_gpu_arm(args):
     targets = [t.to(dev).float() / 255 for t in targets_u8]
     vel_grad = not args.no_vel_grad
     model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
-    trainer = ImageShardedTrainer(model, scene_dev, lr=1e-4, fused=args.fused, sh_chunks=args.sh_chunks, optimizer=args.optimizer)
+    loss_fn = None
+    if args.loss == "photometric":
+        from gsplat.losses import photometric_loss as loss_fn
+    trainer = ImageShardedTrainer(model, scene_dev, lr=1e-4, fused=args.fused, sh_chunks=args.sh_chunks, optimizer=args.optimizer,
+                                  loss_fn=loss_fn)
     H, W, S, N = scene["H"], scene["W"], scene["blur_samples"], scene["N"]
 
     def barrier():
@@ -285,7 +291,8 @@ def run_gpu_arm(args):
     fused_path = None
     if not args.fused and not args.no_fused_path:
         model_f = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
-        trainer_f = ImageShardedTrainer(model_f, scene_dev, lr=1e-4, fused=True, sh_chunks=args.sh_chunks, optimizer=args.optimizer)
+        trainer_f = ImageShardedTrainer(model_f, scene_dev, lr=1e-4, fused=True, sh_chunks=args.sh_chunks, optimizer=args.optimizer,
+                                        loss_fn=loss_fn)
         fsteps = max(20, args.steps // 4)
         for w in range(max(3, args.warmup // 2)):
             trainer_f.train_step(cams[w % n_img], targets[w % n_img], w % n_img)
@@ -514,7 +521,7 @@ def run_gpu_arm(args):
         "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, S={S} blur samples, exposure 1/60 s (synthetic cozyroom stand-in, SURVEY 8d + free space)",
                    "step": "project+SH+bin/sort+blend fwd, L1 (gsplat.losses.l1_loss), full bwd, grad allreduce (N>1), Adam over the flat buffer; 1 image per GPU per step",
                    "optimizer": "gsplat.optim.FlatAdam (b200_adam_step)" if args.optimizer == "b200" else "torch.optim.Adam(fused=True)",
-                   "sh_chunks": args.sh_chunks,
+                   "sh_chunks": args.sh_chunks, "loss": args.loss,
                    "velocity_grad": vel_grad, "global_batch": world,
                    "api": ("gsplat.fused.render_gaussians (raw parameters, caller-modified)" if args.fused else
                            "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians"), "parallelism": f"image-sharded dp{world}",
