@@ -177,8 +177,16 @@ __global__ void __launch_bounds__(SSIM_THREADS) ssim_backward_kernel(const SsimB
     }
 }
 
-static SsimWindow make_window() {
+// SSIM of smooth images is ill-conditioned in the window's normalisation (var = E[x^2] - mu^2 with E[x^2] >> var: a
+// relative error d in sum(w) moves var by ~25 d), so a caller that wants the library's numbers passes the library's own
+// float32 taps (gsplat/losses.py builds them with the same torch ops as pytorch_msssim._fspecial_gauss_1d); the
+// default is the same formula evaluated in float here.
+static SsimWindow make_window(const float *window11) {
     SsimWindow w;
+    if (window11) {
+        for (int k = 0; k < SSIM_WIN; ++k) w.w[k] = window11[k];
+        return w;
+    }
     float sum = 0.f;
     for (int k = 0; k < SSIM_WIN; ++k) {
         const float x = (float)(k - SSIM_WIN / 2);
@@ -206,7 +214,7 @@ extern "C" size_t b200_ssim_maps_bytes(unsigned img_height, unsigned img_width, 
 
 extern "C" int b200_ssim_forward(unsigned img_height, unsigned img_width, unsigned channels, const float *pred,
                                  const float *target, float *maps, float *ssim_out, float *loss_out, const float *l1_loss,
-                                 float ssim_lambda, void *ws, int ws_is_zeroed, void *stream) {
+                                 float ssim_lambda, const float *window11, void *ws, int ws_is_zeroed, void *stream) {
     B200_REQUIRE(img_height >= SSIM_WIN && img_width >= SSIM_WIN, "SSIM needs an image of at least 11 x 11 pixels");
     B200_REQUIRE(channels >= 1 && channels <= 65535, "bad channel count");
     B200_REQUIRE(pred && target && ssim_out && ws, "null pointer");
@@ -220,7 +228,7 @@ extern "C" int b200_ssim_forward(unsigned img_height, unsigned img_width, unsign
     p.ssim_out = ssim_out; p.loss_out = loss_out; p.l1 = l1_loss; p.lambda = ssim_lambda;
     p.inv_count = (float)(1.0 / ((double)p.Ho * (double)p.Wo * (double)p.C));
     p.C1 = 0.01f * 0.01f; p.C2 = 0.03f * 0.03f;  // (K * data_range)^2, data_range = 1
-    p.win = make_window();
+    p.win = make_window(window11);
     cudaStream_t st = as_stream(stream);
     if (!ws_is_zeroed) B200_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st));
     dim3 grid((p.Wo + SSIM_TILE - 1) / SSIM_TILE, (p.Ho + SSIM_TILE - 1) / SSIM_TILE, p.C);
@@ -231,7 +239,8 @@ extern "C" int b200_ssim_forward(unsigned img_height, unsigned img_width, unsign
 
 extern "C" int b200_ssim_backward(unsigned img_height, unsigned img_width, unsigned channels, const float *pred,
                                   const float *target, const float *maps, float scale, const float *add_in,
-                                  float add_scale, const float *v_scale, float *grad, void *stream) {
+                                  float add_scale, const float *v_scale, const float *window11, float *grad,
+                                  void *stream) {
     B200_REQUIRE(img_height >= SSIM_WIN && img_width >= SSIM_WIN, "SSIM needs an image of at least 11 x 11 pixels");
     B200_REQUIRE(channels >= 1 && channels <= 65535, "bad channel count");
     B200_REQUIRE(pred && target && maps && grad, "null pointer");
@@ -241,7 +250,7 @@ extern "C" int b200_ssim_backward(unsigned img_height, unsigned img_width, unsig
     p.pred = pred; p.target = target; p.maps = maps; p.add_in = add_in; p.add_scale = add_scale;
     p.scale = scale * (float)(1.0 / ((double)p.Ho * (double)p.Wo * (double)p.C));
     p.v_scale = v_scale; p.grad = grad;
-    p.win = make_window();
+    p.win = make_window(window11);
     dim3 grid((p.W + SSIM_TILE - 1) / SSIM_TILE, (p.H + SSIM_TILE - 1) / SSIM_TILE, p.C);
     ssim_backward_kernel<<<grid, SSIM_THREADS, 0, as_stream(stream)>>>(p);
     B200_LAUNCH_CHECK();

@@ -53,8 +53,8 @@ SIGNATURES = {
     "b200_adam_step": (_i, [C.c_longlong, _p, _p, _p, _p, _i, _d, _d, _d, _d, _d, _i, _p]),
     "b200_ssim_ws_bytes": (_sz, [_u, _u, _u]),
     "b200_ssim_maps_bytes": (_sz, [_u, _u, _u]),
-    "b200_ssim_forward": (_i, [_u, _u, _u, _p, _p, _p, _p, _p, _p, _f, _p, _i, _p]),
-    "b200_ssim_backward": (_i, [_u, _u, _u, _p, _p, _p, _f, _p, _f, _p, _p, _p]),
+    "b200_ssim_forward": (_i, [_u, _u, _u, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _p]),
+    "b200_ssim_backward": (_i, [_u, _u, _u, _p, _p, _p, _f, _p, _f, _p, _p, _p, _p]),
     "b200_l1_loss_ws_bytes": (_sz, []),
     "b200_l1_loss": (_i, [C.c_longlong, _p, _p, _p, _p, _p, _i, _p]),
     "b200_nd_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -59,6 +59,20 @@ def l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
 # ---- SSIM and the full photometric loss (splatfacto.py:957-975) -------------------------------------------------
 
 _ssim_ws = {}
+_window = None
+
+
+def _window_taps():
+    """The 11 float32 taps exactly as pytorch_msssim builds them (_fspecial_gauss_1d(11, 1.5): float32 arange, exp,
+    normalise), as a ctypes array the C ABI reads on the host."""
+    global _window
+    if _window is None:
+        import ctypes
+        coords = torch.arange(11, dtype=torch.float32) - 11 // 2
+        g = torch.exp(-(coords ** 2) / (2 * 1.5 ** 2))
+        g = g / g.sum()
+        _window = (ctypes.c_float * 11)(*[float(x) for x in g])
+    return _window
 
 
 def _ssim_workspace(dev, H, W, C):
@@ -103,7 +117,7 @@ class _Photometric(Function):
                 check(lib.b200_l1_loss(pred_c.numel(), ptr(pred_c), ptr(target_c), ptr(l1), ptr(g1), ptr(_workspace(dev)), 1,
                                        stream()))
             check(lib.b200_ssim_forward(H, W, C, ptr(pred_c), ptr(target_c), ptr(maps), ptr(ssim_val),
-                                        ptr(out) if lam is not None else None, ptr(l1), float(lam or 0.0),
+                                        ptr(out) if lam is not None else None, ptr(l1), float(lam or 0.0), _window_taps(),
                                         ptr(_ssim_workspace(dev, H, W, C)), 1, stream()))
         ctx.save_for_backward(pred_c, target_c)
         ctx.maps, ctx.g1, ctx.lam = maps, g1, lam
@@ -125,7 +139,7 @@ class _Photometric(Function):
             else:             # (1 - lam) * sign / n - lam * d SSIM / d pred
                 scale, add_in, add_scale = -float(lam), ctx.g1, 1.0 - float(lam)
             check(_lib.load().b200_ssim_backward(H, W, C, ptr(pred_c), ptr(target_c), ptr(ctx.maps), scale, ptr(add_in),
-                                                 add_scale, ptr(v), ptr(grad), stream()))
+                                                 add_scale, ptr(v), _window_taps(), ptr(grad), stream()))
         ctx.maps = ctx.g1 = None
         return grad, None, None
 

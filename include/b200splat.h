@@ -277,15 +277,19 @@ B200_API int b200_l1_loss(long long numel, const float *pred, const float *targe
  *       (l1_loss null = 0); if maps (b200_ssim_maps_bytes bytes): the three partial-derivative maps for the backward.
  *   b200_ssim_backward: grad = [v_scale[0] *] (add_scale * add_in + scale * dSSIM/dpred); add_in, v_scale optional.
  *       With add_in = the L1 cotangent, add_scale = 1 - lambda, scale = -lambda this is the photometric cotangent.
+ * window11: optional HOST float[11], the normalised window taps (null = exp(-x^2 / 4.5) / sum evaluated in float here);
+ *       SSIM of smooth images is sensitive to the last bits of the taps, so a binding that must reproduce
+ *       pytorch_msssim passes the taps that library builds.
  * ws: b200_ssim_ws_bytes bytes, 16-byte aligned, ws_is_zeroed as for b200_l1_loss.  Deterministic. */
 B200_API size_t b200_ssim_ws_bytes(unsigned img_height, unsigned img_width, unsigned channels);
 B200_API size_t b200_ssim_maps_bytes(unsigned img_height, unsigned img_width, unsigned channels);
 B200_API int b200_ssim_forward(unsigned img_height, unsigned img_width, unsigned channels, const float *pred,
                                const float *target, float *maps, float *ssim_out, float *loss_out, const float *l1_loss,
-                               float ssim_lambda, void *ws, int ws_is_zeroed, void *stream);
+                               float ssim_lambda, const float *window11, void *ws, int ws_is_zeroed, void *stream);
 B200_API int b200_ssim_backward(unsigned img_height, unsigned img_width, unsigned channels, const float *pred,
                                 const float *target, const float *maps, float scale, const float *add_in,
-                                float add_scale, const float *v_scale, float *grad, void *stream);
+                                float add_scale, const float *v_scale, const float *window11, float *grad,
+                                void *stream);
 
 /* ---- optimizer ("next" row f-2 of SURVEY section 8) ---------------------------------------------
  * One Adam update (no weight decay, no amsgrad: what nerfstudio/engine/optimizers.py:158-171 builds for every Splatfacto

@@ -1,6 +1,6 @@
 """GPU parity of the fused loss kernels against the CPU oracles: L1 vs torch, SSIM / photometric loss vs
 oracle/ssim_oracle.py (fp64 autograd restatement of pytorch_msssim; parity of that restatement is unpinned, see its
-header).  Tolerances: values 3e-6 absolute (fp32 filtering of 121 taps and E[x^2] - mu^2 in fp32 vs fp64: the library
+header).  Tolerances: values 5e-6 absolute (fp32 filtering of 121 taps and E[x^2] - mu^2 in fp32 vs fp64: the library
 itself is 1e-7 .. 2e-6 off the fp64 result on these images); cotangents 1e-4 of the tensor's max magnitude + 1e-3
 relative (same conditioning)."""
 import pytest
@@ -38,13 +38,13 @@ def test_ssim_and_photometric_loss_vs_oracle(H, W, C, smooth):
     tc = t.cuda()
     out = ssim(pc, tc)
     (g,) = torch.autograd.grad(out, pc)
-    assert abs(float(out) - float(ref_ssim)) <= 3e-6
+    assert abs(float(out) - float(ref_ssim)) <= 5e-6
     tol = 1e-4 * float(g_ssim.abs().max())
     torch.testing.assert_close(g.cpu().double(), g_ssim, rtol=1e-3, atol=tol)
 
     loss = photometric_loss(pc, tc, 0.2)
     (gl,) = torch.autograd.grad(loss * 1.7, pc)
-    assert abs(float(loss) - float(ref_loss)) <= 3e-6
+    assert abs(float(loss) - float(ref_loss)) <= 5e-6
     # the L1 part of the cotangent is +-1/n exactly; at |p - t| ~ 0 fp32 and fp64 may pick different signs: none here
     torch.testing.assert_close(gl.cpu().double(), g_loss, rtol=1e-3, atol=1e-4 * float(g_loss.abs().max()))
     # deterministic
