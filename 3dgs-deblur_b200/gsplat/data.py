@@ -7,7 +7,7 @@ per-frame intrinsics, top-level `exposure_time` / `rolling_shutter_time` (second
 the pose scale factor, :334-336), "up" orientation + "poses" centring (cameras/camera_utils.py:520-628), auto scale to
 the unit box (:268-274), train/eval split (data/utils/dataparsers_utils.py:23-43) and output-resolution rescale (:353).
 Pinned against the reference parser itself: tests/golden/make_golden_data.py runs it on fabricated datasets and
-tests/test_data_cpu.py compares.
+tests/test_data_cpu.py compares.  `load_ply_points` reads the seed cloud (`sparse_pc.ply`) into the same frame.
 
 `to_gsplat_camera` is the camera block of Splatfacto.get_outputs (nerfstudio/models/splatfacto.py:733-747,799-800):
 OpenGL camera-to-world -> gsplat world-to-camera (flip y and z), velocities rotated by the same flip.
@@ -202,6 +202,67 @@ def load_transforms(path: str, split: str = "train", *, scale_factor: float = 1.
         fx=f32(fx), fy=f32(fy), cx=f32(cx), cy=f32(cy), height=size(height), width=size(width),
         velocities=velocities, exposure_time=meta.get("exposure_time"), rolling_shutter_time=meta.get("rolling_shutter_time"),
         dataparser_scale=scale_out, dataparser_transform=transform_out, indices=idx)
+
+
+_PLY_TYPES = {"char": "i1", "uchar": "u1", "int8": "i1", "uint8": "u1", "short": "i2", "ushort": "u2", "int16": "i2",
+              "uint16": "u2", "int": "i4", "uint": "u4", "int32": "i4", "uint32": "u4", "float": "f4", "float32": "f4",
+              "double": "f8", "float64": "f8"}
+
+
+def load_ply_points(path: str, dataparser_transform=None, dataparser_scale: float = 1.0):
+    """Seed point cloud (`sparse_pc.ply`, `ply_file_path` in transforms.json) -> (xyz (n,3) f32, rgb (n,3) u8), moved
+    into the dataparser's output frame like nerfstudio_dataparser.py:469-491 does: [xyz 1] @ transform^T, then * scale.
+    Reads ascii and binary_little_endian vertex elements with x, y, z (+ red, green, blue); no external PLY library."""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError("not a PLY file")
+        fmt, n_vertex, props, in_vertex = None, 0, [], False
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError("PLY header without end_header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok:
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                in_vertex = tok[1] == "vertex"
+                if in_vertex:
+                    n_vertex = int(tok[2])
+                elif n_vertex and not props:
+                    raise ValueError("PLY vertex element without properties")
+            elif tok[0] == "property" and in_vertex:
+                if tok[1] == "list":
+                    raise ValueError("list properties on vertices are not supported")
+                props.append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == "end_header":
+                break
+        names = [nme for nme, _ in props]
+        if not all(k in names for k in ("x", "y", "z")):
+            raise ValueError("PLY vertices need x, y, z")
+        if fmt == "ascii":
+            rows = np.loadtxt(f, max_rows=n_vertex, ndmin=2)
+            cols = {nme: rows[:, i] for i, nme in enumerate(names)}
+        elif fmt == "binary_little_endian":
+            dt = np.dtype([(nme, "<" + t) for nme, t in props])
+            data = np.frombuffer(f.read(dt.itemsize * n_vertex), dtype=dt, count=n_vertex)
+            cols = {nme: data[nme] for nme in names}
+        else:
+            raise ValueError(f"unsupported PLY format: {fmt}")
+    xyz = np.stack([cols["x"], cols["y"], cols["z"]], axis=1).astype(np.float32)
+    if all(k in cols for k in ("red", "green", "blue")):
+        rgb = np.stack([cols["red"], cols["green"], cols["blue"]], axis=1)
+        if rgb.dtype.kind == "f" and rgb.max(initial=0) <= 1.0:
+            rgb = rgb * 255
+        rgb = rgb.astype(np.uint8)
+    else:
+        rgb = np.full((xyz.shape[0], 3), 128, np.uint8)
+    if dataparser_transform is not None:
+        T = np.asarray(dataparser_transform, np.float32)
+        xyz = (np.concatenate([xyz, np.ones_like(xyz[:, :1])], axis=1) @ T.T).astype(np.float32)
+    xyz = xyz * np.float32(dataparser_scale)
+    return xyz, rgb
 
 
 def to_gsplat_camera(camera_to_world, velocity=None) -> Dict[str, torch.Tensor]:

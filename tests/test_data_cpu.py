@@ -85,3 +85,37 @@ def test_to_gsplat_camera_is_the_splatfacto_camera_block():
     with pytest.raises(RuntimeError):
         from gsplat.data import ImagePrefetcher
         ImagePrefetcher([torch.zeros(4, 4, 3, dtype=torch.uint8)], [torch.zeros(21)], "cpu")
+
+
+def test_load_ply_points_ascii_and_binary(tmp_path):
+    """sparse_pc.ply seed cloud: both encodings, then [xyz 1] @ T^T * scale (nerfstudio_dataparser.py:469-491)."""
+    from gsplat.data import load_ply_points
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(size=(37, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, (37, 3)).astype(np.uint8)
+    header = "ply\nformat {fmt} 1.0\ncomment test\nelement vertex 37\nproperty float x\nproperty float y\nproperty float z\n" \
+             "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face 0\nproperty list uchar int vertex_indices\nend_header\n"
+    a = tmp_path / "a.ply"
+    with open(a, "w") as f:
+        f.write(header.format(fmt="ascii"))
+        for p_, c_ in zip(xyz, rgb):
+            f.write("%r %r %r %d %d %d\n" % (float(p_[0]), float(p_[1]), float(p_[2]), c_[0], c_[1], c_[2]))
+    b = tmp_path / "b.ply"
+    rec = np.zeros(37, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+    rec["x"], rec["y"], rec["z"] = xyz.T
+    rec["red"], rec["green"], rec["blue"] = rgb.T
+    with open(b, "wb") as f:
+        f.write(header.format(fmt="binary_little_endian").encode())
+        f.write(rec.tobytes())
+    T = np.concatenate([np.linalg.qr(rng.normal(size=(3, 3)))[0], rng.normal(size=(3, 1))], axis=1).astype(np.float32)
+    want = (np.concatenate([xyz, np.ones((37, 1), np.float32)], 1) @ T.T) * 0.37
+    for path in (a, b):
+        got_xyz, got_rgb = load_ply_points(str(path), T, 0.37)
+        np.testing.assert_allclose(got_xyz, want, rtol=1e-5, atol=1e-6)
+        assert np.array_equal(got_rgb, rgb)
+    raw_xyz, _ = load_ply_points(str(b))
+    np.testing.assert_array_equal(raw_xyz, xyz)
+    bad = tmp_path / "bad.ply"
+    bad.write_text("plx\n")
+    with pytest.raises(ValueError):
+        load_ply_points(str(bad))
