@@ -9,7 +9,7 @@ python -m pytest tests -m gpu -q 2>&1 | tail -8
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || tail -c 1500 gpurun_out/${TAG}_bench.err
 python bench.py --no-cpu-baseline --loss photometric --steps 200 > gpurun_out/${TAG}_bench_photometric.json 2>/dev/null
 python bench.py --no-cpu-baseline --fused --steps 200 > gpurun_out/${TAG}_bench_fused.json 2>/dev/null
-python - <<'PY'
+python - <<PY
 import json
 for f in ("${TAG}_bench", "${TAG}_bench_photometric", "${TAG}_bench_fused"):
     d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
