@@ -75,3 +75,16 @@ def test_operators_raise_on_cpu_tensors():
         gsplat.spherical_harmonics(0, torch.zeros(4, 3), torch.zeros(4, 1, 3))
     with pytest.raises(RuntimeError, match="CUDA"):
         gsplat.compute_cov2d_bounds(torch.ones(4, 3))
+    # the loss / optimizer / dispatcher helpers are CUDA-only as well
+    from gsplat.data import ImagePrefetcher
+    from gsplat.losses import l1_loss, photometric_loss
+    from gsplat.optim import FlatAdam
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        l1_loss(torch.zeros(16, 16, 3), torch.zeros(16, 16, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        photometric_loss(torch.zeros(16, 16, 3), torch.zeros(16, 16, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FlatAdam(torch.zeros(8), torch.zeros(8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ImagePrefetcher([torch.zeros(4, 4, 3, dtype=torch.uint8)], [torch.zeros(21)], "cpu")
