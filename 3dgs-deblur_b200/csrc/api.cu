@@ -26,8 +26,8 @@ namespace b200 {
 // (pixels evaluated side by side with masked updates, 96 registers, 5 CTAs per SM).
 // B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD = 1 select the one-pixel kernels.
 int blend_pixels_per_lane(bool backward) {
-    static const int fwd = [] { const char *e = getenv("B200_BLEND_PPL_FWD"); return (e && e[0] == '1') ? 1 : 2; }();
-    static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '1') ? 1 : 2; }();
+    static const int fwd = [] { const char *e = getenv("B200_BLEND_PPL_FWD"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : 2; }();
+    static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : 2; }();
     return backward ? bwd : fwd;
 }
 }  // namespace b200

@@ -61,7 +61,7 @@ __device__ __forceinline__ float butterfly16(const float (&v)[16], int lane) {
 }
 
 template <int S, int PPL>
-__global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : 3) blend_backward_kernel(const BlendBwdParams p) {
+__global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 ? 6 : 3)) blend_backward_kernel(const BlendBwdParams p) {
     constexpr int NT = BLEND_THREADS / PPL;
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : 3) blend_b
 
 template <int S>
 static int launch_bwd(const BlendBwdParams &p, cudaStream_t st) {
-    if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2)
+    if (p.g.bw == 16 && blend_pixels_per_lane(true) == 4)  // experimental (B200_BLEND_PPL_BWD=4)
+        blend_backward_kernel<S, 4><<<p.g.tbx * p.g.tby, BLEND_THREADS / 4, 0, st>>>(p);
+    else if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2)
         blend_backward_kernel<S, 2><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
     else
         blend_backward_kernel<S, 1><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);

@@ -110,6 +110,11 @@ template <int PPL>
 __device__ __forceinline__ void tile_pixel_ppl(int bw, int tid, int p, int &lx, int &ly, bool &has_pixel) {
     if (PPL == 1) {
         tile_pixel(bw, tid, lx, ly, has_pixel);
+    } else if (PPL == 4) {  // experimental: 2 warps per 16x16 tile, each a 16x8 block, 4 pixels per lane
+        const int w = tid >> 5, lane = tid & 31;
+        lx = (lane & 7) + ((p & 1) << 3);
+        ly = (w << 3) + (lane >> 3) + 4 * (p >> 1);
+        has_pixel = true;
     } else {
         const int w = tid >> 5, lane = tid & 31;
         lx = ((w & 1) << 3) + (lane & 7);

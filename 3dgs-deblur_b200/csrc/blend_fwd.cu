@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
 template <int S>
 static int launch_fwd(const BlendFwdParams &p, cudaStream_t st) {
     // two pixels per lane when the tile is the full 16x16 (the only size Splatfacto uses, splatfacto.py:815)
-    if (p.g.bw == 16 && blend_pixels_per_lane(false) == 2)
+    if (p.g.bw == 16 && blend_pixels_per_lane(false) == 4)  // experimental (B200_BLEND_PPL_FWD=4)
+        blend_forward_kernel<S, 4><<<p.g.tbx * p.g.tby, BLEND_THREADS / 4, 0, st>>>(p);
+    else if (p.g.bw == 16 && blend_pixels_per_lane(false) == 2)
         blend_forward_kernel<S, 2><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
     else
         blend_forward_kernel<S, 1><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
