@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200splat.so")
+LIB_PATH = os.environ.get("B200SPLAT_LIB") or os.path.join(_HERE, "lib", "libb200splat.so")  # override: A/B of builds
 
 _p, _i, _u, _f, _d, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_double, C.c_size_t
 
