@@ -114,3 +114,63 @@ def test_nan_inputs_keep_the_pair():
         bad[k] = one(np.nan)
         assert per_sample(**bad, exposure=1 / 60, S=5)[0], k
         assert closed_form(**bad, exposure=1 / 60, S=5)[0], k
+
+
+# ---- the packed record's cull data (csrc/blend_common.cuh: make_record) ---------------------------------------
+
+def record_extents(a, b, c, opac):
+    """thr = ln(255 opac); (hx, hy) = padded half extents of {sigma <= thr}; -1 = can never contribute; inf = unbounded."""
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        thr = np.log(f32(255) * opac).astype(f32)
+        det = (a * c - b * b).astype(f32)
+        tm = (f32(2) * (thr * f32(1.00001) + f32(1e-4)) / det).astype(f32)
+        hx = (np.sqrt(tm * c) * f32(1.00001) + f32(1e-3)).astype(f32)
+        hy = (np.sqrt(tm * a) * f32(1.00001) + f32(1e-3)).astype(f32)
+        never = (thr < 0) | (opac <= 0)
+        bounded = (det > 0) & (a > 0) & (c > 0)
+        hx = np.where(never, f32(-1), np.where(bounded, hx, f32(np.inf))).astype(f32)
+        hy = np.where(never, f32(-1), np.where(bounded, hy, f32(np.inf))).astype(f32)
+        thr = np.where(never, f32(-1), thr).astype(f32)
+    return thr, hx, hy
+
+
+def test_record_extents_never_exclude_a_contributing_pixel():
+    """Whenever the reference's exact per-pixel test lets a Gaussian contribute (sigma >= 0 and alpha = min(.999, opac
+    exp(-sigma)) >= 1/255, forward.cu:411-419), the offset lies inside the record's box and sigma is below the kernels'
+    `thr + 1e-4` short-cut -- so neither the per-warp cull, nor the tile cull, nor the ex2 skip can drop it."""
+    rng = np.random.default_rng(7)
+    n = 2_000_000
+    s1, s2 = 10.0 ** rng.uniform(-0.5, 2.5, n), 10.0 ** rng.uniform(-0.5, 2.5, n)  # principal std devs in pixels
+    th = rng.uniform(0, np.pi, n)
+    ca, sa = np.cos(th), np.sin(th)
+    a = (ca * ca / s1 ** 2 + sa * sa / s2 ** 2).astype(f32)
+    c = (sa * sa / s1 ** 2 + ca * ca / s2 ** 2).astype(f32)
+    b = (ca * sa * (1 / s1 ** 2 - 1 / s2 ** 2)).astype(f32)
+    kind = rng.integers(0, 10, n)
+    b[kind == 0] *= f32(3)          # some indefinite conics (the reference blends them where sigma >= 0)
+    a[kind == 1] = -a[kind == 1]
+    opac = np.where(kind == 2, 10.0 ** rng.uniform(-4, -2, n), rng.uniform(0.003, 1.0, n)).astype(f32)
+    thr, hx, hy = record_extents(a, b, c, opac)
+    # offsets: on and around the alpha = 1/255 contour (direction random), plus uniform ones
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        phi = rng.uniform(0, 2 * np.pi, n)
+        ux, uy = np.cos(phi), np.sin(phi)
+        q = 0.5 * (a * ux * ux + c * uy * uy) + b * ux * uy
+        rad = np.sqrt(np.maximum(thr, 0) / np.where(q > 0, q, np.nan)) * rng.uniform(0.9, 1.05, n)
+        rad = np.where(np.isfinite(rad), rad, rng.uniform(0, 200, n))
+        dx, dy = (rad * ux).astype(f32), (rad * uy).astype(f32)
+        sigma = (f32(0.5) * (a * dx * dx + c * dy * dy) + b * dx * dy).astype(f32)
+        alpha = np.minimum(f32(0.999), opac * np.exp(-sigma.astype(np.float64)))
+        contributes = (sigma >= 0) & (alpha >= 1.0 / 255.0 * (1 - 1e-6))  # a hair generous: covers the ex2.approx error
+    assert int(contributes.sum()) > 200_000
+    inside = (np.abs(dx) <= hx) & (np.abs(dy) <= hy)
+    bad = contributes & ~inside
+    assert not bad.any(), f"{int(bad.sum())} contributing offsets outside the cull box, e.g. {int(np.flatnonzero(bad)[0])}"
+    bad2 = contributes & (sigma > thr + f32(1e-4))
+    assert not bad2.any(), f"{int(bad2.sum())} contributing offsets above the sigma short-cut"
+    # and the box is tight where float32 can tell (aspect ratio <= 5, so a*c - b*b does not cancel): exact extent + 1 %
+    ok = (hx > 0) & np.isfinite(hx) & (kind > 2) & (np.maximum(s1, s2) <= 5 * np.minimum(s1, s2))
+    det = a.astype(np.float64) * c - b.astype(np.float64) ** 2
+    with np.errstate(invalid="ignore", divide="ignore"):
+        exact_hx = np.sqrt(2 * np.maximum(thr, 0).astype(np.float64) * c / det)
+    assert int(ok.sum()) > 100_000 and np.all(hx[ok] <= exact_hx[ok] * 1.01 + 0.01)
