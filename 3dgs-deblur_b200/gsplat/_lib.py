@@ -70,20 +70,19 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if True:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"libb200splat.so not found at {LIB_PATH}. Build it with "
-                "`python 3dgs-deblur_b200/build.py` (needs nvcc); there is no CPU fallback."
-            )
-        lib = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
-            fn.restype = res
-            fn.argtypes = args
-        if lib.b200_abi_version() != 1:
-            raise RuntimeError("libb200splat.so ABI version mismatch; rebuild it")
-        _LIB = lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libb200splat.so not found at {LIB_PATH}. Build it with "
+            "`python 3dgs-deblur_b200/build.py` (needs nvcc); there is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b200_abi_version() != 1:
+        raise RuntimeError("libb200splat.so ABI version mismatch; rebuild it")
+    _LIB = lib
     return _LIB
 
 

@@ -88,3 +88,20 @@ def test_operators_raise_on_cpu_tensors():
         FlatAdam(torch.zeros(8), torch.zeros(8))
     with pytest.raises(RuntimeError, match="CUDA"):
         ImagePrefetcher([torch.zeros(4, 4, 3, dtype=torch.uint8)], [torch.zeros(21)], "cpu")
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No silent fallback: with the shared library absent every entry point raises, naming the build command."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import torch, gsplat\n"
+            "from gsplat import _lib\n"
+            "try:\n"
+            "    _lib.load()\n"
+            "except RuntimeError as e:\n"
+            "    assert 'not found' in str(e) and 'no CPU fallback' in str(e), e\n"
+            "    print('LOUD')\n" % os.path.join(ROOT, "3dgs-deblur_b200"))
+    env = dict(os.environ, B200SPLAT_LIB=str(tmp_path / "nope" / "libb200splat.so"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "LOUD" in r.stdout, r.stdout + r.stderr
