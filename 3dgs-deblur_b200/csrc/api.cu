@@ -24,7 +24,8 @@ namespace b200 {
 // Measured on B200 (tools/blend_probe.py, culled lists, config 2 / 3 / 4): two pixels per lane take the forward from
 // 472 / 2926 / 4527 us to 448 / 2285 / 3355 us and the backward from 864 / 4086 / 7641 us to 779 / 3414 / 6440 us
 // (pixels evaluated side by side with masked updates, 96 registers, 5 CTAs per SM).
-// B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD = 1 select the one-pixel kernels.
+// B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD = 1 select the one-pixel kernels, 4 the experimental four-pixel ones (slower at
+// config 2).
 int blend_pixels_per_lane(bool backward) {
     static const int fwd = [] { const char *e = getenv("B200_BLEND_PPL_FWD"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : 2; }();
     static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : 2; }();
