@@ -7,6 +7,7 @@ import os
 import socket
 import sys
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -37,7 +38,7 @@ def _fake_render(model, cam, scene, cam_index=0, sh_degree_to_use=3):
     return img, img[..., 0], p["means"][:, :2], torch.ones(p["means"].shape[0], dtype=torch.int32)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, sh_chunks):
     sys.path.insert(0, os.path.join(ROOT, "3dgs-deblur_b200"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -50,7 +51,8 @@ def _worker(rank, world, port, out):
     # parameter views alias the flat buffer, gradient views alias the flat gradient buffer
     model.params["means"].data[0, 0] = 7.0
     assert model.flat[0] == 7.0
-    tr = dp.ImageShardedTrainer(model, scene, lr=1e-2, loss_fn=_torch_l1, optimizer="torch")
+    tr = dp.ImageShardedTrainer(model, scene, lr=1e-2, loss_fn=_torch_l1, optimizer="torch", sh_chunks=sh_chunks)
+    assert len(tr._chunks) == 1 + sh_chunks
     assert [tr.image_index(s, 4) for s in range(3)] == [(s * world + rank) % 4 for s in range(3)]
     cams = [dict(w=float(i + 1)) for i in range(4)]
     for step in range(3):
@@ -59,7 +61,7 @@ def _worker(rank, world, port, out):
     # replicas identical after 3 steps although every rank saw different images
     gathered = [torch.zeros_like(model.flat) for _ in range(world)]
     dist.all_gather(gathered, model.flat)
-    assert torch.equal(gathered[0], gathered[1])
+    assert all(torch.equal(gathered[0], g_) for g_ in gathered[1:])
     # the overlapped exchange (SH slice reduced from the autograd hook) gives the same parameters as the plain one
     model2 = dp.FlatGaussians(scene, "cpu", n_cameras=4, optimize_velocities=True)
     model2.params["means"].data[0, 0] = 7.0  # same aliasing probe as the first model
@@ -80,15 +82,19 @@ def _worker(rank, world, port, out):
     v = torch.ones(50) * (rank + 1)
     mx = torch.ones(50) * (rank + 1)
     g, v, mx = tr.reduce_densify_stats(g, v, mx)
-    assert torch.all(g == 3) and torch.all(v == 3) and torch.all(mx == 2)
+    tot = world * (world + 1) // 2
+    assert torch.all(g == tot) and torch.all(v == tot) and torch.all(mx == world)
     if rank == 0:
         torch.save(model.flat.clone(), out)
     dist.destroy_process_group()
 
 
-def test_image_sharded_trainer_world2_gloo(tmp_path):
+@pytest.mark.parametrize("world,sh_chunks", [(2, 1), (3, 3)])
+def test_image_sharded_trainer_gloo(tmp_path, world, sh_chunks):
+    """world 2 with the default exchange (geometry chunk + one SH chunk) and world 3 with the SH block in 3 chunks: the
+    chunked, overlapped exchange ends at the same parameters as the plain one, replicas stay identical."""
     out = str(tmp_path / "flat.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, sh_chunks), nprocs=world, join=True)
     flat = torch.load(out)
     assert torch.isfinite(flat).all()
 
