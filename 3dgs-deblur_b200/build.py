@@ -12,16 +12,19 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
+# A/B builds of kernel variants: B200_BUILD_VARIANT=<tag> B200_NVCC_FLAGS="-D..." writes gsplat/lib/libb200splat_<tag>.so
+# (objects in csrc/_obj_<tag>/); load it with B200SPLAT_LIB=<path> (gsplat/_lib.py).
+VARIANT = os.environ.get("B200_BUILD_VARIANT", "")
+OBJ = os.path.join(CSRC, "_obj" + ("_" + VARIANT if VARIANT else ""))
 LIB_DIR = os.path.join(HERE, "gsplat", "lib")
-LIB = os.path.join(LIB_DIR, "libb200splat.so")
+LIB = os.path.join(LIB_DIR, "libb200splat" + ("_" + VARIANT if VARIANT else "") + ".so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("B200_NVCC_FLAGS", "").split()
 
 
 def _sources():

@@ -187,11 +187,13 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
                     const float cut = C.w + 1e-4f;
                     float sxx = 0.f, sxy = 0.f, syy = 0.f, gxs = 0.f, gys = 0.f, gxa = 0.f, gya = 0.f, pvx = 0.f, pvy = 0.f,
                           vop = 0.f;
-                    float cdot[PPL], facsum[PPL];
+                    float cdot[PPL], facsum[PPL], dx0[PPL], dy0[PPL];
+                    const SigmaEntry se = sigma_entry(A, Bq);
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
                         cdot[q] = C.x * vo[q][0] + C.y * vo[q][1] + C.z * vo[q][2];
                         facsum[q] = 0.f;
+                        dx0[q] = A.x - px[q]; dy0[q] = A.y - py[q];
                     }
                     bool any = false;
 #pragma unroll
@@ -204,9 +206,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
 #pragma unroll
                         for (int q = 0; q < PPL; ++q) {
                             tau[q] = blur[s] + roll[q];
-                            dx[q] = A.x + tau[q] * A.z - px[q];
-                            dy[q] = A.y + tau[q] * A.w - py[q];
-                            sigma[q] = 0.5f * (Bq.x * dx[q] * dx[q] + Bq.z * dy[q] * dy[q]) + Bq.y * dx[q] * dy[q];
+                            sigma_eval(se, px[q], py[q], dx0[q], dy0[q], tau[q], dx[q], dy[q], sigma[q]);
                             ok[q] = (idx <= bin_final[q][s]) && !(sigma[q] > cut || sigma[q] < 0.f);  // backward.cu:252-254,276
                             some |= ok[q];
                         }

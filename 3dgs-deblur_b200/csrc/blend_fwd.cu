@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
                     const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
                     const float cut = C.w + 1e-4f;
+                    const SigmaEntry se = sigma_entry(A, Bq);
+                    float dx0[PPL], dy0[PPL];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) { dx0[q] = A.x - px[q]; dy0[q] = A.y - py[q]; }
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         if (!(smask & (1u << s))) continue;  // warp-uniform
@@ -132,9 +136,8 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
                         for (int q = 0; q < PPL; ++q) {
                             if (!(alive[q] & (1u << s))) continue;
                             const float tau = blur[s] + roll[q];
-                            const float dx = A.x + tau * A.z - px[q];
-                            const float dy = A.y + tau * A.w - py[q];
-                            const float sigma = 0.5f * (Bq.x * dx * dx + Bq.z * dy * dy) + Bq.y * dx * dy;
+                            float dx, dy, sigma;
+                            sigma_eval(se, px[q], py[q], dx0[q], dy0[q], tau, dx, dy, sigma);
                             if (sigma > cut || sigma < 0.f) continue;  // alpha < 1/255 guaranteed above thr
                             const float alpha = fminf(0.999f, Bq.w * exp_neg_approx(sigma));
                             if (alpha < 1.f / 255.f) continue;
