@@ -7,7 +7,8 @@ in this image, so this file restates its published algorithm (pytorch_msssim/ssi
 `gaussian_filter`, `_ssim`, `ssim`) in plain torch; gradients come from autograd.  **Parity unpinned**: there is no
 reference output or fixture to check this restatement against; it is anchored on the package's documented defaults
 (win_size 11, win_sigma 1.5, K = (0.01, 0.03), valid padding, filtering along H then W, mean over channel and space,
-`nonnegative_ssim=False`) and on the reference's call site.
+`nonnegative_ssim=False`) and on the reference's call site; tests/test_ssim_oracle_cpu.py cross-checks it against an
+independent scipy.ndimage implementation of the textbook definition.
 """
 import torch
 import torch.nn.functional as F
