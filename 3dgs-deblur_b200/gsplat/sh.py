@@ -1,46 +1,46 @@
-"""`gsplat.sh` -- spherical-harmonics colours (operator surface of the reference's gsplat/sh.py:1-104)."""
-from typing import Literal
-
-from torch import Tensor
+"""`gsplat.sh` -- view-dependent colours from spherical-harmonics coefficients, behind the operator surface of the
+reference's gsplat/sh.py:1-104 (`num_sh_bases`, `deg_from_sh`, `spherical_harmonics`)."""
 from torch.autograd import Function
 
 import gsplat.cuda as _C
 
-_BASES = {0: 1, 1: 4, 2: 9, 3: 16}
-_DEGREE = {1: 0, 4: 1, 9: 2, 16: 3, 25: 4}
+_METHODS = ("poly", "fast")
+_BASES_OF_DEGREE = (1, 4, 9, 16, 25)  # (degree + 1)^2 for degree 0 .. 4, the kernel maximum
 
 
 def num_sh_bases(degree: int):
-    return _BASES.get(degree, 25)
+    """Number of coefficient triples of a degree-`degree` expansion; anything above 3 counts as the maximum, 4."""
+    return _BASES_OF_DEGREE[degree] if 0 <= degree <= 3 else _BASES_OF_DEGREE[4]
 
 
 def deg_from_sh(num_bases: int):
-    assert num_bases in _DEGREE, "Invalid number of SH bases"
-    return _DEGREE[num_bases]
+    assert num_bases in _BASES_OF_DEGREE, "Invalid number of SH bases"
+    return _BASES_OF_DEGREE.index(num_bases)
 
 
-def spherical_harmonics(degrees_to_use: int, viewdirs: Tensor, coeffs: Tensor,
-                        method: Literal["poly", "fast"] = "fast") -> Tensor:
-    """Colours (N,3) from un-normalised view directions (N,3) and coefficients (N,K,3).
+def spherical_harmonics(degrees_to_use, viewdirs, coeffs, method="fast"):
+    """(N,3) colours from un-normalised view directions (N,3) and coefficients (N,K,3), K in {1,4,9,16,25}.
 
-    Differentiable w.r.t. `coeffs` only, like the reference (sh.py:45-46)."""
+    Only the first `num_sh_bases(degrees_to_use)` bases are evaluated (Splatfacto ramps the degree up during training).
+    `method` selects the basis formulation: "poly" (monomials) or "fast" (recurrences).  The gradient flows to `coeffs`
+    only -- view directions are treated as constants, as in the reference (sh.py:45-46)."""
     assert coeffs.shape[-2] >= num_sh_bases(degrees_to_use)
-    assert method in ["poly", "fast"]
-    return _SphericalHarmonics.apply(method, degrees_to_use, viewdirs.contiguous(), coeffs.contiguous())
+    assert method in _METHODS
+    return _SHColors.apply(method, degrees_to_use, viewdirs.contiguous(), coeffs.contiguous())
 
 
-class _SphericalHarmonics(Function):
+class _SHColors(Function):
     @staticmethod
     def forward(ctx, method, degrees_to_use, viewdirs, coeffs):
-        ctx.degrees_to_use = degrees_to_use
-        ctx.degree = deg_from_sh(coeffs.shape[-2])
-        ctx.method = method
+        degree = deg_from_sh(coeffs.shape[-2])
+        ctx.cfg = (method, degree, degrees_to_use)
         ctx.save_for_backward(viewdirs)
-        return _C.compute_sh_forward(method, coeffs.shape[0], ctx.degree, degrees_to_use, viewdirs, coeffs)
+        return _C.compute_sh_forward(method, coeffs.shape[0], degree, degrees_to_use, viewdirs, coeffs)
 
     @staticmethod
-    def backward(ctx, v_colors):
+    def backward(ctx, grad_colors):
+        method, degree, degrees_to_use = ctx.cfg
         (viewdirs,) = ctx.saved_tensors
-        v_coeffs = _C.compute_sh_backward(ctx.method, v_colors.shape[0], ctx.degree, ctx.degrees_to_use, viewdirs,
-                                          v_colors.contiguous())
-        return None, None, None, v_coeffs
+        grad_coeffs = _C.compute_sh_backward(method, grad_colors.shape[0], degree, degrees_to_use, viewdirs,
+                                             grad_colors.contiguous())
+        return None, None, None, grad_coeffs  # method, degrees_to_use, viewdirs, coeffs
