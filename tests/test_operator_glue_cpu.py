@@ -209,3 +209,20 @@ def test_project_gaussians_glue(monkeypatch):
         project_gaussians(means, scales, 1.0, quats.detach() * 2, None, None, 0, 0.0, viewmat, 50.0, 50.0, 32.0, 24.0, 48, 64, 16)
     with pytest.raises(AssertionError, match="block_width"):
         project_gaussians(means, scales, 1.0, quats, None, None, 0, 0.0, viewmat, 50.0, 50.0, 32.0, 24.0, 48, 64, 1)
+
+
+def test_fakes_have_the_real_wrappers_arity():
+    """The fakes above stand in for gsplat.cuda wrappers: same number of positional parameters, so a plumbing mistake
+    in the glue cannot hide behind a more permissive fake."""
+    import inspect
+    import gsplat.cuda as _C
+    expected = dict(pack_records=5, bin_cull=10, blend_forward_packed=11, blend_backward_packed=15, bin_tiles=7,
+                    nd_rasterize_forward=14, nd_rasterize_backward=18, compute_sh_forward=6, compute_sh_backward=6)
+    for name, n in expected.items():
+        params = [p for p in inspect.signature(getattr(_C, name)).parameters.values()
+                  if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+        assert len(params) == n, (name, [p.name for p in params])
+    fwd = inspect.signature(_C.project_gaussians_forward).parameters
+    bwd = inspect.signature(_C.project_gaussians_backward).parameters
+    assert list(fwd)[:18][-1] == "clip_thresh" and "_vel_tensors" in fwd and "_quat_flag" in fwd
+    assert all(k in bwd for k in ("_vel_tensors", "_exact", "_want_vel", "_want_viewmat", "_want_cov"))
