@@ -9,6 +9,9 @@ the unit box (:268-274), train/eval split (data/utils/dataparsers_utils.py:23-43
 Pinned against the reference parser itself: tests/golden/make_golden_data.py runs it on fabricated datasets and
 tests/test_data_cpu.py compares.  `load_ply_points` reads the seed cloud (`sparse_pc.ply`) into the same frame.
 
+`load_image_u8` / `composite_u8` read and composite a training image like the reference's dataset and model do
+(data/datasets/base_dataset.py:61-110, models/splatfacto.py:900-923).
+
 `to_gsplat_camera` is the camera block of Splatfacto.get_outputs (nerfstudio/models/splatfacto.py:733-747,799-800):
 OpenGL camera-to-world -> gsplat world-to-camera (flip y and z), velocities rotated by the same flip.
 
@@ -263,6 +266,39 @@ def load_ply_points(path: str, dataparser_transform=None, dataparser_scale: floa
         xyz = (np.concatenate([xyz, np.ones_like(xyz[:, :1])], axis=1) @ T.T).astype(np.float32)
     xyz = xyz * np.float32(dataparser_scale)
     return xyz, rgb
+
+
+def load_image_u8(path: str, alpha_color=None) -> torch.Tensor:
+    """One training image as an (H, W, 3) or (H, W, 4) uint8 tensor, the way the reference's dataset reads it
+    (nerfstudio/data/datasets/base_dataset.py:61-79, 95-110): greyscale is repeated to three channels; with `alpha_color`
+    (three floats in [0, 1]) an RGBA image is composited over that colour and comes back with three channels, otherwise
+    the alpha channel is kept for the model to composite against its own background (splatfacto.py:912-923)."""
+    from PIL import Image
+
+    with Image.open(path) as im:
+        a = np.array(im, dtype="uint8")
+    if a.ndim == 2:
+        a = np.repeat(a[:, :, None], 3, axis=2)
+    if a.ndim != 3 or a.shape[2] not in (3, 4):
+        raise ValueError(f"Image shape of {a.shape} is incorrect.")
+    img = torch.from_numpy(a)
+    if alpha_color is not None and img.shape[-1] == 4:
+        col = torch.as_tensor(alpha_color, dtype=torch.float32)
+        if not bool(((col >= 0) & (col <= 1)).all()):
+            raise ValueError("alpha color given is out of range between [0, 1].")
+        alpha = img[:, :, -1:] / 255.0
+        img = torch.clamp(img[:, :, :3] * alpha + 255.0 * col * (1.0 - alpha), min=0, max=255).to(torch.uint8)
+    return img.contiguous()
+
+
+def composite_u8(image_u8: torch.Tensor, background: torch.Tensor) -> torch.Tensor:
+    """Float target image in [0, 1] from a uint8 image; an alpha channel is composited over `background` (3 floats)
+    like Splatfacto does per step (splatfacto.py:900-923): alpha * rgb + (1 - alpha) * background."""
+    img = image_u8.float() / 255.0
+    if img.shape[2] == 4:
+        alpha = img[..., -1:]
+        return alpha * img[..., :3] + (1 - alpha) * background
+    return img
 
 
 def to_gsplat_camera(camera_to_world, velocity=None) -> Dict[str, torch.Tensor]:

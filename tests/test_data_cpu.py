@@ -119,3 +119,32 @@ def test_load_ply_points_ascii_and_binary(tmp_path):
     bad.write_text("plx\n")
     with pytest.raises(ValueError):
         load_ply_points(str(bad))
+
+
+def test_load_image_u8_and_compositing(tmp_path):
+    """Greyscale -> 3 channels, RGBA kept or composited over alpha_color (base_dataset.py:61-110), per-step compositing
+    against a background (splatfacto.py:912-923)."""
+    from PIL import Image
+    from gsplat.data import composite_u8, load_image_u8
+    rng = np.random.default_rng(1)
+    rgba = rng.integers(0, 256, (6, 5, 4)).astype(np.uint8)
+    Image.fromarray(rgba, "RGBA").save(tmp_path / "a.png")
+    Image.fromarray(rgba[:, :, 0], "L").save(tmp_path / "g.png")
+    Image.fromarray(rgba[:, :, :3], "RGB").save(tmp_path / "c.png")
+    keep = load_image_u8(str(tmp_path / "a.png"))
+    assert keep.dtype == torch.uint8 and np.array_equal(keep.numpy(), rgba)
+    assert np.array_equal(load_image_u8(str(tmp_path / "c.png")).numpy(), rgba[:, :, :3])
+    grey = load_image_u8(str(tmp_path / "g.png")).numpy()
+    assert grey.shape == (6, 5, 3) and np.array_equal(grey[:, :, 1], rgba[:, :, 0])
+    col = torch.tensor([0.2, 0.5, 1.0])
+    flat = load_image_u8(str(tmp_path / "a.png"), alpha_color=col)
+    f = torch.from_numpy(rgba)  # the reference's uint8 formula, base_dataset.py:102-110
+    want = torch.clamp(f[:, :, :3] * (f[:, :, -1:] / 255.0) + 255.0 * col * (1.0 - f[:, :, -1:] / 255.0), min=0, max=255).to(torch.uint8)
+    assert torch.equal(flat, want)
+    bg = torch.tensor([0.1, 0.9, 0.3])
+    tgt = composite_u8(keep, bg)
+    a = f[..., -1:].float() / 255
+    torch.testing.assert_close(tgt, a * (f[..., :3].float() / 255) + (1 - a) * bg)
+    assert torch.equal(composite_u8(torch.from_numpy(rgba[:, :, :3].copy()), bg), torch.from_numpy(rgba[:, :, :3].copy()).float() / 255)
+    with pytest.raises(ValueError):
+        load_image_u8(str(tmp_path / "a.png"), alpha_color=[0.0, 2.0, 0.0])
