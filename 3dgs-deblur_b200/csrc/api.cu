@@ -32,6 +32,16 @@ int blend_pixels_per_lane(bool backward) {
     return backward ? bwd : fwd;
 }
 }  // namespace b200
+#ifdef B200_BLEND_COUNTERS
+namespace b200 { __device__ unsigned long long g_blend_counters[16]; }
+// A/B builds only: read (and optionally clear) the blend kernels' execution counters (blend_common.cuh)
+extern "C" __attribute__((visibility("default"))) int b200_blend_counters(unsigned long long *out16_host, int reset) {
+    cudaDeviceSynchronize();
+    if (out16_host) cudaMemcpyFromSymbol(out16_host, b200::g_blend_counters, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(b200::g_blend_counters, z, sizeof(z)); }
+    return 0;
+}
+#endif
 extern "C" long long b200_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
 extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
 extern "C" const char *b200_last_error(void) { return b200::g_err; }

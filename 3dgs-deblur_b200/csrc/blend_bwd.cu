@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
         }
     };
 
+    B200_COUNT_DECL;
     if (nb > 0) issue(0);
     for (int b = 0; b < nb; ++b) {
         const int st = b & 1;
@@ -173,13 +174,15 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int e = c0 + lane;
                 const unsigned my_mask =
-                    ((e < cnt) && (top - e <= wmax)) ? sample_mask<S>(s_rec[st][e], win, p.g.exposure) : 0u;
+                    ((e < cnt) && (top - e <= wmax)) ? sample_mask_exact<S>(s_rec[st][e], win, p.g.exposure) : 0u;
                 unsigned m = __ballot_sync(0xffffffffu, my_mask != 0u);
+                if ((e < cnt) && (top - e <= wmax)) B200_COUNT(0, 1);
                 while (m) {
                     const int src = __ffs(m) - 1;
                     const int k = c0 + src;
                     m &= m - 1;
                     const unsigned smask = __shfl_sync(0xffffffffu, my_mask, src);
+                    if (lane == 0) { B200_COUNT(1, 1); B200_COUNT(2, __popc(smask)); }
                     const int idx = top - k;
                     const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
                             sigma_eval(se, px[q], py[q], dx0[q], dy0[q], tau[q], dx[q], dy[q], sigma[q]);
                             ok[q] = (idx <= bin_final[q][s]) && !(sigma[q] > cut || sigma[q] < 0.f);  // backward.cu:252-254,276
                             some |= ok[q];
+                            if (inside[q]) B200_COUNT(3, 1);
                         }
                         if (!some) continue;
                         float vis[PPL], ov[PPL], alpha[PPL];
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
                             alpha[q] = fminf(0.99f, ov[q]);
                             ok[q] = ok[q] && !(alpha[q] < 1.f / 255.f);
                             some |= ok[q];
+                            if (ok[q]) B200_COUNT(4, 1);
                         }
                         if (!some) continue;
                         any = true;
@@ -249,6 +254,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
                         vr += facsum[q] * vo[q][0]; vg += facsum[q] * vo[q][1]; vb += facsum[q] * vo[q][2];
                     }
                     if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
+                    if (lane == 0) B200_COUNT(5, 1);
                     const float v[16] = {vr, vg, vb, 0.5f * sxx, sxy, 0.5f * syy, gxs, gys, gxa, gya, pvx, pvy, vop,
                                          0.f, 0.f, 0.f};
                     const float tot = butterfly16(v, lane);
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
         }
         __syncthreads();  // stage `st` is refilled two batches from now
     }
+    B200_COUNT_FLUSH(8);
 }
 
 template <int S>

@@ -12,6 +12,30 @@ constexpr int BLEND_STAGES = 2;
 // 16x16 tiles can use 2)
 int blend_pixels_per_lane(bool backward);
 
+// -DB200_BLEND_COUNTERS (A/B build only, see tools/blend_counters.py): the blend kernels count what they execute --
+//   [0] tile-list entries tested by a warp cull   [1] warp visits (entries that survive it)
+//   [2] sample blocks entered (warp, entry, sample)  [3] pixel-sample evaluations executed (sigma computed for a live pixel)
+//   [4] evaluations passing the sigma / alpha >= 1/255 tests (the ones that change a pixel or a gradient)
+//   [5] visits that reach the gradient reduction (backward) / blend at least one pixel (forward)
+// forward in slots 0..7, backward in slots 8..15.
+#ifdef B200_BLEND_COUNTERS
+extern __device__ unsigned long long g_blend_counters[16];
+#define B200_COUNT(slot, n) (cnt_[(slot)] += (unsigned long long)(n))
+#define B200_COUNT_DECL unsigned long long cnt_[6] = {0, 0, 0, 0, 0, 0}
+#define B200_COUNT_FLUSH(base)                                                             \
+    do {                                                                                   \
+        _Pragma("unroll") for (int c_ = 0; c_ < 6; ++c_) {                                 \
+            unsigned long long v_ = cnt_[c_];                                              \
+            _Pragma("unroll") for (int o_ = 16; o_ > 0; o_ >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, o_); \
+            if ((threadIdx.x & 31) == 0 && v_) atomicAdd(&g_blend_counters[(base) + c_], v_); \
+        }                                                                                  \
+    } while (0)
+#else
+#define B200_COUNT(slot, n) ((void)0)
+#define B200_COUNT_DECL ((void)0)
+#define B200_COUNT_FLUSH(base) ((void)0)
+#endif
+
 struct BlendGeom {
     int H, W, bw, tbx, tby;
     float rs_time, exposure;
@@ -35,7 +59,9 @@ __device__ __forceinline__ PackedGaussian make_record(int id, float x, float y, 
     g.pad = 0.f;
     const float thr = logf(255.f * g.opac);  // opac <= 0 -> -inf / NaN
     g.thr = thr;
-    const float det = g.ca * g.cc - g.cb * g.cb;
+    // a*c - b*b cancels for needle-shaped splats (eigenvalue ratio ~1e5 at 45 degrees loses two digits in fp32, which
+    // would shrink the box by percents): form it in double, once per Gaussian
+    const float det = (float)((double)g.ca * (double)g.cc - (double)g.cb * (double)g.cb);
     if (thr < 0.f || g.opac <= 0.f) {
         g.hx = -1.f; g.hy = -1.f;  // alpha < 1/255 wherever sigma >= 0: can never contribute
         g.thr = -1.f;
@@ -212,6 +238,61 @@ __device__ __forceinline__ unsigned sample_mask(const PackedGaussian &g, const W
         const bool out = (cx0 - g.hx > w.x1) || (cx1 + g.hx < w.x0) || (cy0 - g.hy > w.y1) || (cy1 + g.hy < w.y0);
         m |= out ? 0u : (1u << s);
     }
+    return m;
+}
+
+// Exact refinement of the box tests above.  For a positive-definite conic, can sigma(d) = (a dx^2 + c dy^2)/2 + b dx dy
+// reach `thr` anywhere in the box of offsets [x0,x1] x [y0,y1]?  sigma is convex with its minimum (0) at the origin, so
+// unless the box contains the origin the minimum over the box lies on one of its four edges, where sigma is a 1-D
+// parabola whose clamped vertex is closed-form.  The box of offsets is the Gaussian's swept centre minus the pixel
+// rectangle -- a superset of the offsets the blend evaluates, so "cannot reach" is a proof that no pixel centre of the
+// rectangle passes the reference's `alpha < 1/255` skip (forward.cu:417).  The (hx, hy) box alone keeps every elongated
+// splat whose bounding box touches the rectangle; this keeps it only where the ellipse itself does.
+// Margins: the blend's fp32 sigma carries rounding of ~1e-7 relative to its LARGEST term (the three terms cancel for
+// needle-shaped splats), so the comparison allows 2e-5 of that magnitude + 1e-3; NaNs keep the entry.
+#ifndef B200_EXACT_CULL
+#define B200_EXACT_CULL 1
+#endif
+__device__ __forceinline__ bool box_may_reach(float a, float b, float c, float inv_a, float inv_c, float thr, float x0,
+                                              float x1, float y0, float y1) {
+    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;
+    float best = __int_as_float(0x7f800000);
+    {
+        const float t0 = fminf(fmaxf(-b * x0 * inv_c, y0), y1), t1 = fminf(fmaxf(-b * x1 * inv_c, y0), y1);
+        best = fminf(best, 0.5f * (a * x0 * x0 + c * t0 * t0) + b * x0 * t0);
+        best = fminf(best, 0.5f * (a * x1 * x1 + c * t1 * t1) + b * x1 * t1);
+    }
+    {
+        const float t0 = fminf(fmaxf(-b * y0 * inv_a, x0), x1), t1 = fminf(fmaxf(-b * y1 * inv_a, x0), x1);
+        best = fminf(best, 0.5f * (a * t0 * t0 + c * y0 * y0) + b * t0 * y0);
+        best = fminf(best, 0.5f * (a * t1 * t1 + c * y1 * y1) + b * t1 * y1);
+    }
+    const float mx = fmaxf(fabsf(x0), fabsf(x1)), my = fmaxf(fabsf(y0), fabsf(y1));
+    const float mag = 0.5f * (a * mx * mx + c * my * my) + fabsf(b) * mx * my;
+    return !(best > thr + (2e-5f * mag + 1e-3f));
+}
+
+// sample_mask + the exact refinement for the surviving samples (bounded, positive-definite conics only: the record
+// carries finite extents exactly then).
+template <int S>
+__device__ __forceinline__ unsigned sample_mask_exact(const PackedGaussian &g, const WarpWindow &w, float exposure) {
+    unsigned m = sample_mask<S>(g, w, exposure);
+#if B200_EXACT_CULL
+    if (m == 0u || !(g.hx < 3.0e38f)) return m;
+    const float inv_a = 1.0f / g.ca, inv_c = 1.0f / g.cc;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        if (!(m & (1u << s))) continue;
+        const float b = blur_offset<S>(s, exposure);
+        const float t0 = b + w.r0, t1 = b + w.r1;
+        const float ax = t0 * g.vx, bx = t1 * g.vx, ay = t0 * g.vy, by = t1 * g.vy;
+        const float x0 = (g.x + fminf(ax, bx)) - w.x1, x1 = (g.x + fmaxf(ax, bx)) - w.x0;
+        const float y0 = (g.y + fminf(ay, by)) - w.y1, y1 = (g.y + fmaxf(ay, by)) - w.y0;
+        // (the differences above are rounded: widen the box by a hair so it still contains every evaluated offset)
+        const float ex = 1e-6f * (fabsf(g.x) + fabsf(w.x0) + fabsf(w.x1)) + 1e-4f, ey = 1e-6f * (fabsf(g.y) + fabsf(w.y0) + fabsf(w.y1)) + 1e-4f;
+        if (!box_may_reach(g.ca, g.cb, g.cc, inv_a, inv_c, g.thr, x0 - ex, x1 + ex, y0 - ey, y1 + ey)) m &= ~(1u << s);
+    }
+#endif
     return m;
 }
 

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
         return a != 0u;
     };
 
+    B200_COUNT_DECL;
     int b = 0;
     bool pending = false;
     if (nb > 0) { issue(0); pending = true; }
@@ -114,13 +115,18 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
         if (__any_sync(0xffffffffu, any_alive())) {
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int e = c0 + lane;
-                const unsigned my_mask = (e < cnt) ? sample_mask<S>(s_rec[st][e], win, p.g.exposure) : 0u;
+                const unsigned my_mask = (e < cnt) ? sample_mask_exact<S>(s_rec[st][e], win, p.g.exposure) : 0u;
                 unsigned m = __ballot_sync(0xffffffffu, my_mask != 0u);
+                if (e < cnt) B200_COUNT(0, 1);
                 while (m) {
                     const int src = __ffs(m) - 1;
                     const int k = c0 + src;
                     m &= m - 1;
                     const unsigned smask = __shfl_sync(0xffffffffu, my_mask, src);
+                    if (lane == 0) { B200_COUNT(1, 1); B200_COUNT(2, __popc(smask)); }
+#ifdef B200_BLEND_COUNTERS
+                    bool blended_ = false;
+#endif
                     const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
                     const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
@@ -138,9 +144,14 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
                             const float tau = blur[s] + roll[q];
                             float dx, dy, sigma;
                             sigma_eval(se, px[q], py[q], dx0[q], dy0[q], tau, dx, dy, sigma);
+                            B200_COUNT(3, 1);
                             if (sigma > cut || sigma < 0.f) continue;  // alpha < 1/255 guaranteed above thr
                             const float alpha = fminf(0.999f, Bq.w * exp_neg_approx(sigma));
                             if (alpha < 1.f / 255.f) continue;
+                            B200_COUNT(4, 1);
+#ifdef B200_BLEND_COUNTERS
+                            blended_ = true;
+#endif
                             const float next_T = T[q][s] * (1.f - alpha);
                             if (next_T <= 1e-4f) {  // forward.cu:421-427: this sample is done, entry not blended
                                 alive[q] &= ~(1u << s);
@@ -152,6 +163,9 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
                             last[q][s] = start + k;
                         }
                     }
+#ifdef B200_BLEND_COUNTERS
+                    if (__any_sync(0xffffffffu, blended_) && lane == 0) B200_COUNT(5, 1);
+#endif
                     if (!__any_sync(0xffffffffu, any_alive())) { m = 0; c0 = cnt; }
                 }
             }
@@ -160,6 +174,7 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
         if (!__syncthreads_or(any_alive())) { ++b; break; }
     }
     if (pending && b < nb) mbar_wait(&s_bar[b & 1], (uint32_t)((b >> 1) & 1));  // drain the prefetch before exit
+    B200_COUNT_FLUSH(0);
 
     const float bg0 = __ldg(p.background), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
 #pragma unroll

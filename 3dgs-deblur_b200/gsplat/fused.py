@@ -58,8 +58,11 @@ class _FusedRender(Function):
         tens = [t.contiguous() for t in (means, log_scales, quats, opacity_logit, sh_dc, sh_rest, viewmat, cam_pos)]
         means, log_scales, quats, opacity_logit, sh_dc, sh_rest, viewmat, cam_pos = tens
         _lib.require_cuda(*tens)
-        lin_d = lin.detach().reshape(-1)[:3].contiguous().float()
-        ang_d = ang.detach().reshape(-1)[:3].contiguous().float()
+        if lin.numel() < 3 or ang.numel() < 3:
+            raise ValueError("render_gaussians: camera velocities need 3 components each")
+        # velocities may live on the host (the reference's camera code builds them there): the kernels take device pointers
+        lin_d = lin.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:3].contiguous()
+        ang_d = ang.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:3].contiguous()
         with _lib.on_device(dev):
             packed = torch.empty((n * lib.b200_packed_record_bytes(),), dtype=torch.uint8, device=dev)
             depths = torch.empty((n,), dtype=torch.float32, device=dev)
@@ -81,6 +84,7 @@ class _FusedRender(Function):
         ctx.cfg, ctx.K, ctx.total = cfg, K, total
         ctx.grad_sink, ctx.info = grad_sink, info
         ctx.vel_shapes = (lin.shape, ang.shape)
+        ctx.vel_devs = (lin.device, ang.device)
         ctx.save_for_backward(means, log_scales, quats, opacity_logit, sh_dc, sh_rest, viewmat, cam_pos, lin_d, ang_d, bg,
                               packed, radii, ids, bins, Ts, fi)
         info["radii"] = radii
@@ -131,8 +135,8 @@ class _FusedRender(Function):
         if want_vm:
             v_viewmat = torch.zeros_like(viewmat)
             v_viewmat[..., :3, :4] = g_vm
-        v_lin = g_lin.reshape(ctx.vel_shapes[0]) if (want_vel and ctx.needs_input_grad[8]) else None
-        v_ang = g_ang.reshape(ctx.vel_shapes[1]) if (want_vel and ctx.needs_input_grad[9]) else None
+        v_lin = g_lin.reshape(ctx.vel_shapes[0]).to(ctx.vel_devs[0]) if (want_vel and ctx.needs_input_grad[8]) else None
+        v_ang = g_ang.reshape(ctx.vel_shapes[1]).to(ctx.vel_devs[1]) if (want_vel and ctx.needs_input_grad[9]) else None
         v_bg = None
         if ctx.needs_input_grad[10]:
             v_bg = torch.matmul(v_rgb.float().reshape(-1, 3).t(), Ts.mean(dim=-1).float().reshape(-1, 1)).squeeze()

@@ -86,6 +86,7 @@ class _ProjectGaussians(Function):
 
         ctx.cfg = (num_points, glob_scale, fx, fy, cx, cy, img_height, img_width, rolling_shutter_time, exposure_time)
         ctx.vel_shapes = (linear_velocity.shape, angular_velocity.shape)
+        ctx.vel_devs = (linear_velocity.device, angular_velocity.device)  # host-side camera velocities get host gradients
         ctx.vel_grad = bool(linear_velocity.requires_grad or angular_velocity.requires_grad)
         ctx.save_for_backward(means3d, scales, quats, viewmat, cov3d, radii, conics, compensation, lin, ang)
         ctx.mark_non_differentiable(radii, num_tiles_hit)
@@ -106,8 +107,8 @@ class _ProjectGaussians(Function):
         v_lin = v_ang = v_viewmat = None
         if want_vel:
             g_lin, g_ang = rest.pop(0), rest.pop(0)
-            v_lin = g_lin.reshape(ctx.vel_shapes[0]) if ctx.needs_input_grad[4] else None
-            v_ang = g_ang.reshape(ctx.vel_shapes[1]) if ctx.needs_input_grad[5] else None
+            v_lin = g_lin.reshape(ctx.vel_shapes[0]).to(ctx.vel_devs[0]) if ctx.needs_input_grad[4] else None
+            v_ang = g_ang.reshape(ctx.vel_shapes[1]).to(ctx.vel_devs[1]) if ctx.needs_input_grad[5] else None
         if want_vm:
             g = rest.pop(0)  # (3,4)
             v_viewmat = torch.zeros_like(viewmat)

@@ -26,6 +26,42 @@ for _p in (ROOT, os.path.join(ROOT, "3dgs-deblur_b200")):
 METRIC = "train images/sec (fwd+bwd) at N=5 blur samples"
 
 
+def workload_string(cfg, N, W, H, S):
+    """One spelling of the workload for every arm (the driver compares the arms' `config.workload`)."""
+    return f"{cfg}: {N} Gaussians, {W}x{H}, S={S} blur samples (synthetic stand-in of SURVEY 8d + free space around the cameras)"
+
+
+def bench_config(cfg, N, W, H, S):
+    """`config` of the JSON line: identical for every arm run on the same workload (arm-specific facts go to `details`)."""
+    return {"workload": workload_string(cfg, N, W, H, S),
+            "step": "1 image per GPU per step: projection + SH + tile binning + blur blend forward, L1 loss, full backward",
+            "l2": "no explicit flush: the per-step working set (59 floats x N x {param, grad, 2 Adam moments} = %d MB, + the "
+                  "images) exceeds the 126 MB L2 and every step renders a different camera" % (59 * N * 16 // 2**20)}
+
+
+def usable_cores():
+    """Host threads this process may really use: the affinity mask, capped by a cgroup CPU quota if one is set (a
+    128-thread OpenMP team on a 16-CPU quota is throttled, not faster)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -109,35 +145,33 @@ def cpu_step_factory(cfg, n_override=None):
 
 
 def run_cpu_arm(args, one_shot=False):
-    """Times the oracle port on all host cores.  A step is the full image when K + W such steps fit the time budget
-    (B200_CPU_ARM_BUDGET_S, default 150 s for the whole run, 10 s for the one-shot baseline); otherwise a BOUNDED SAMPLE:
-    the blend forward + backward on a centred band of image rows (time scaled by H / band) and, when even the
-    per-Gaussian stages (projection, SH, binning; ~0.4 s) exceed the per-step budget, those stages are timed every m-th
-    step and their last measured time is charged to the steps in between.  The sample is stated in the JSON."""
-    cores = int(os.environ.get("B200_CPU_THREADS", os.cpu_count() or 1))
-    # all host cores: torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently make this a 1-thread
-    # baseline; the oracle's OpenMP runtime reads the variable when liboracle.so is loaded (below), so override it here
+    """Times the oracle port on the host cores.  The sample is a function of the ARGUMENTS only (never of how fast the
+    box happens to be), so two runs of the same command time the same work: with at most 40 steps (warm-up included)
+    every step is the full image; beyond that the blend forward + backward runs on a centred band of image rows whose
+    height shrinks with the step count (time scaled by H / band) and the per-Gaussian stages (projection, SH, binning)
+    run in full every m-th step with their last measured time charged in between.  The sample is stated in the JSON.
+    Threads: B200_CPU_THREADS, else every core this process may use (affinity mask / cgroup quota)."""
+    cores = int(os.environ.get("B200_CPU_THREADS", usable_cores()))
+    # torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently make this a 1-thread baseline; the oracle's
+    # OpenMP runtime reads the variable when liboracle.so is loaded (below), so override it here
     os.environ["OMP_NUM_THREADS"] = str(cores)
     step, d = cpu_step_factory(args.config, args.n)
     from oracle import oracle as _O
     cores = _O.set_threads(cores)  # the count the OpenMP runtime actually uses
     H = d["H"]
     n_steps = 1 if one_shot else args.steps + args.warmup
-    budget = float(os.environ.get("B200_CPU_ARM_BUDGET_S", "10" if one_shot else "150")) / max(n_steps, 1)
-    pre, blend = step(rows=(0, min(H, 64)))  # calibration band (4 tile rows)
-    blend_full = blend * H / min(H, 64)
+    full_steps = 40
     rows, pre_every = None, 1
     sample = f"1 image = full {d['W']}x{H} config-{args.config} fwd+bwd (projection, SH, binning, blend) per step"
-    if pre + blend_full > budget:
-        blend_budget = max(budget - pre, 0.25 * budget)
-        band = int(min(H, max(16, (H * blend_budget / blend_full) // 16 * 16)))
+    if n_steps > full_steps:
+        band = int(min(H, max(16, (H * full_steps // n_steps) // 16 * 16)))
         if band < H:
             rows = (H // 2 - band // 2, H // 2 - band // 2 + band)
-        if pre > 0.5 * budget:
-            pre_every = int(min(n_steps, max(2, round(pre / (0.5 * budget)))))
+        pre_every = int(-(-n_steps // full_steps))
         sample = (f"per step: blend fwd+bwd on image rows {rows[0] if rows else 0}..{rows[1] if rows else H} of {H} (time x "
                   f"{H / (rows[1] - rows[0]) if rows else 1:.2f}); per-Gaussian stages (projection, SH, binning) "
-                  + ("in full every step" if pre_every == 1 else f"in full every {pre_every}th step, last measured time charged in between"))
+                  f"in full every {pre_every}th step, last measured time charged in between")
+    pre = 0.0
     scale = 1.0 if rows is None else H / (rows[1] - rows[0])
     state = {"pre": pre, "k": 0}
 
@@ -167,9 +201,8 @@ def run_cpu_arm(args, one_shot=False):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": f"{args.config}: {d['N']} Gaussians, {d['W']}x{H}, S={d['S']} blur samples (synthetic cozyroom stand-in)",
-                   "arm": "CPU oracle port of the reference kernels (oracle/splat_oracle.c), OpenMP over image rows",
-                   "wall_s": wall},
+        "config": bench_config(args.config, d["N"], d["W"], H, d["S"]),
+        "details": {"arm": "CPU oracle port of the reference kernels (oracle/splat_oracle.c), OpenMP over image rows", "wall_s": wall},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -264,27 +297,39 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- kernel-resident metric: inputs already in HBM, CUDA-event timing, max over ranks
-    for w in range(args.warmup):
+    # warm-up: at least one pass over every training image, so no timed step meets a new camera (first-use allocations,
+    # list capacities) -- args.warmup is a lower bound
+    n_warm = max(args.warmup, n_img + 2)
+    for w in range(n_warm):
         trainer.train_step(cams[w % n_img], targets[w % n_img], w % n_img)
-    barrier()
+    # the clock sampler forks nvidia-smi: start it BEFORE the barrier that opens the timed region (round 1 started it
+    # on rank 0 after the barrier, so the other ranks waited for rank 0's fork/exec inside their first allreduce and
+    # that latency was charged to the max-over-ranks time)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        time.sleep(0.3)  # first samples in hand before the region opens
+    barrier()
+    # one event per step boundary: total = last - first (what `value` uses), per-step spread shows one-off stalls
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     l0 = lib.b200_launch_count()
-    ev0.record()
+    evs[0].record()
     for k in range(args.steps):
         i = k % n_img
         trainer.train_step(cams[i], targets[i], i)
-    ev1.record()
+        evs[k + 1].record()
     barrier()
     launches = (lib.b200_launch_count() - l0) / args.steps
-    ms = ev0.elapsed_time(ev1) / args.steps
+    ms = evs[0].elapsed_time(evs[-1]) / args.steps
+    per_step = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps))
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
+    t = torch.tensor([ms, per_step[len(per_step) // 2], per_step[min(len(per_step) - 1, int(0.99 * len(per_step)))], per_step[-1]],
+                     device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, p50, p99, pmax = (float(x) for x in t.tolist())
+    step_ms = {"p50": round(p50, 4), "p99": round(p99, 4), "max": round(pmax, 4),
+               "note": "per-step device time between consecutive events on the compute stream, max over ranks of each statistic"}
     value = world * 1000.0 / ms
 
     # ---- the same step through the caller-modified fused operator, reported beside the drop-in number
@@ -478,7 +523,6 @@ def run_gpu_arm(args):
             kernels["bin_cull"]["note"] = "includes its host sync; algorithmic bytes are those of the reference's binning"
             on_path = [k for k in kernels if "note" not in kernels[k] or k == "bin_cull"]
             dom = max(on_path, key=lambda k: kernels[k]["ms"])
-            walk = int(((bins[:, 1] - bins[:, 0]).long().sum().item()) * 256 * S)
             traffic, traffic_src, issue = None, None, None
             tp = os.path.join(ROOT, "profiles", "traffic.json")  # per-launch figures from the committed ncu --set full captures
             if os.path.exists(tp) and args.n is None:
@@ -499,9 +543,7 @@ def run_gpu_arm(args):
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                         "frac": round(kernels[dom]["gbs"] / peak, 5), "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": peak_src, "issue": issue,
-                        "note": ("blend kernels are FP32-issue/MUFU/SHFL/atomic bound, not HBM bound (SURVEY 0.5): "
-                                 "pixel-Gaussian-sample evaluations upper bound per launch = %d -> %.3g eval/s" % (
-                                     walk, walk / (kernels[dom]["ms"] * 1e-3))),
+                        "note": "blend kernels are FP32-issue / MUFU / SHFL / atomic bound, not HBM bound (SURVEY 0.5); see `issue`",
                         "intersections": I, "culled_list_entries": M, "visible": V}
 
     if rank != 0:
@@ -517,16 +559,15 @@ def run_gpu_arm(args):
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, S={S} blur samples, exposure 1/60 s (synthetic cozyroom stand-in, SURVEY 8d + free space)",
-                   "step": "project+SH+bin/sort+blend fwd, L1 (gsplat.losses.l1_loss), full bwd, grad allreduce (N>1), Adam over the flat buffer; 1 image per GPU per step",
-                   "optimizer": "gsplat.optim.FlatAdam (b200_adam_step)" if args.optimizer == "b200" else "torch.optim.Adam(fused=True)",
-                   "sh_chunks": args.sh_chunks, "loss": args.loss,
-                   "velocity_grad": vel_grad, "global_batch": world,
-                   "api": ("gsplat.fused.render_gaussians (raw parameters, caller-modified)" if args.fused else
-                           "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians"), "parallelism": f"image-sharded dp{world}",
-                   "l2": "per-step working set (59 floats x N x {param,grad,2 Adam moments} = %d MB) exceeds the 126 MB L2; no explicit flush" % (59 * N * 16 // 2**20)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+        "data": "synthetic", "warmup_run": n_warm,
+        "config": bench_config(args.config, N, W, H, S),
+        "details": {"step": "project+SH+bin/sort+blend fwd, L1 (gsplat.losses.l1_loss), full bwd, grad allreduce (N>1), Adam over the flat buffer; 1 image per GPU per step",
+                    "optimizer": "gsplat.optim.FlatAdam (b200_adam_step)" if args.optimizer == "b200" else "torch.optim.Adam(fused=True)",
+                    "sh_chunks": args.sh_chunks, "loss": args.loss, "velocity_grad": vel_grad, "global_batch": world,
+                    "api": ("gsplat.fused.render_gaussians (raw parameters, caller-modified)" if args.fused else
+                            "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians"),
+                    "parallelism": f"image-sharded dp{world}"},
+        "step_ms": step_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
     if fused_path:

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(extra_env):
-    env = dict(os.environ, B200_CPU_ARM_BUDGET_S="6", **extra_env)
+    env = dict(os.environ, **extra_env)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c1", "--steps", "1",
                         "--warmup", "1"], env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -28,7 +28,12 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and "sample" in cb
-    assert cb["cores"] == (os.cpu_count() or 1)  # not the launcher's OMP_NUM_THREADS=1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert cb["cores"] == bench.usable_cores()  # every core this process may use, not the launcher's OMP_NUM_THREADS=1
+    # the sample is a function of the arguments only (same command => same work on every box)
+    assert cb["sample"].startswith("1 image = full 256x256 config-c1")
+    assert d["config"] == bench.bench_config("c1", 10000, 256, 256, 1)  # the GPU arm prints the same `config`
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
 

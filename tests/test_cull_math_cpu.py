@@ -122,7 +122,7 @@ def record_extents(a, b, c, opac):
     """thr = ln(255 opac); (hx, hy) = padded half extents of {sigma <= thr}; -1 = can never contribute; inf = unbounded."""
     with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
         thr = np.log(f32(255) * opac).astype(f32)
-        det = (a * c - b * b).astype(f32)
+        det = (a.astype(np.float64) * c.astype(np.float64) - b.astype(np.float64) ** 2).astype(f32)  # double, like make_record
         tm = (f32(2) * (thr * f32(1.00001) + f32(1e-4)) / det).astype(f32)
         hx = (np.sqrt(tm * c) * f32(1.00001) + f32(1e-3)).astype(f32)
         hy = (np.sqrt(tm * a) * f32(1.00001) + f32(1e-3)).astype(f32)
@@ -174,3 +174,35 @@ def test_record_extents_never_exclude_a_contributing_pixel():
     with np.errstate(invalid="ignore", divide="ignore"):
         exact_hx = np.sqrt(2 * (np.maximum(thr, 0).astype(np.float64) + 2e-4) * c / det)  # (+ the 1e-4 sigma margin)
     assert int(ok.sum()) > 100_000 and np.all(hx[ok] <= exact_hx[ok] * 1.01 + 0.01)
+
+
+def test_record_extents_hold_at_the_tangent_points_of_needle_splats():
+    """Needle-shaped splats (eigenvalue ratio up to 1e6, any rotation): the offsets where the alpha = 1/255 contour touches
+    its bounding box are the ones a too-small box would lose first.  a*c - b*b cancels there, so make_record forms it in
+    double; with the float32 product the box comes out up to percents too small."""
+    rng = np.random.default_rng(11)
+    n = 500_000
+    s1 = 10.0 ** rng.uniform(-0.5, 0.5, n)
+    s2 = s1 * 10.0 ** rng.uniform(1.5, 3.0, n)
+    th = np.where(rng.random(n) < 0.5, np.pi / 4, rng.uniform(0, np.pi, n))
+    ca, sa = np.cos(th), np.sin(th)
+    a = (ca * ca / s1 ** 2 + sa * sa / s2 ** 2).astype(f32)
+    c = (sa * sa / s1 ** 2 + ca * ca / s2 ** 2).astype(f32)
+    b = (ca * sa * (1 / s1 ** 2 - 1 / s2 ** 2)).astype(f32)
+    opac = rng.uniform(0.01, 1.0, n).astype(f32)
+    thr, hx, hy = record_extents(a, b, c, opac)
+    A, B, C = a.astype(np.float64), b.astype(np.float64), c.astype(np.float64)
+    det = A * C - B * B
+    ok = (det > 0) & (thr > 0) & np.isfinite(hx)
+    assert int(ok.sum()) > 300_000
+    with np.errstate(invalid="ignore", divide="ignore"):
+        t = np.maximum(thr.astype(np.float64), 0) * rng.uniform(0.97, 1.0, n)   # on / just inside the contour
+        ex = np.sqrt(2 * t * C / det)                                            # extreme x of {sigma = t}
+        for dx, dy in ((ex, -B / C * ex), (-B / A * np.sqrt(2 * t * A / det), np.sqrt(2 * t * A / det))):
+            dx32, dy32 = dx.astype(f32), dy.astype(f32)
+            sigma = (f32(0.5) * (a * dx32 * dx32 + c * dy32 * dy32) + b * dx32 * dy32).astype(f32)
+            alpha = np.minimum(f32(0.999), opac * np.exp(-sigma.astype(np.float64)))
+            contributes = ok & (sigma >= 0) & (alpha >= 1.0 / 255.0)
+            inside = (np.abs(dx32) <= hx) & (np.abs(dy32) <= hy)
+            assert int(contributes.sum()) > 50_000
+            assert not (contributes & ~inside).any(), int((contributes & ~inside).sum())

@@ -77,6 +77,77 @@ def _run_reference_cuda(ref, d):
     return {k: v.detach().cpu().numpy() for k, v in out.items()}
 
 
+ND_CHANNELS = 5
+
+
+def _nd_inputs(d):
+    g = np.random.default_rng(21)
+    return dict(nd_colors=g.uniform(0, 1, (d["N"], ND_CHANNELS)).astype(np.float32),
+                nd_background=g.uniform(0, 1, ND_CHANNELS).astype(np.float32),
+                nd_v_out=g.standard_normal((d["H"], d["W"], ND_CHANNELS)).astype(np.float32),
+                nd_v_alpha=g.standard_normal((d["H"], d["W"])).astype(np.float32))
+
+
+def _run_reference_cuda_nd(ref, d, refout):
+    """The reference's N-channel kernels (forward.cu:185-304, backward.cu:22-141) on the binning state of `refout`:
+    C = 5 channels, fp16 accumulators, no blur (bindings.cu:506-682; rasterize.py:165,245 select them for C != 3)."""
+    H, W = d["H"], d["W"]
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    nd = _nd_inputs(d)
+    opac = cu((d["opacity"][:, 0] * refout["compensation"])[:, None].astype(np.float32))
+    args = (cu(refout["gaussian_ids_sorted"]), cu(refout["tile_bins"]), cu(refout["xys"]), cu(refout["pix_vels"]), 0.0, 0.0,
+            cu(refout["conics"]), cu(nd["nd_colors"]), opac, cu(nd["nd_background"]))
+    img, Ts, fi = ref.nd_rasterize_forward(tb, (16, 16, 1), (W, H, 1), 1, *args)
+    bw = ref.nd_rasterize_backward(H, W, 16, 1, *args, Ts, fi, cu(nd["nd_v_out"]), cu(nd["nd_v_alpha"]))
+    torch.cuda.synchronize()
+    out = dict(nd_img=img, nd_final_Ts=Ts, nd_final_idx=fi, nd_v_xy=bw[0], nd_v_xy_abs=bw[1], nd_v_conic=bw[3],
+               nd_v_colors=bw[4], nd_v_opacity=bw[5])
+    return {k: v.detach().cpu().numpy() for k, v in out.items()}
+
+
+def _nd_check(refout, d, who, fwd, bwd):
+    """An implementation of the N-channel blend against the reference kernels' outputs.  The reference accumulates the
+    image in fp16 (forward.cu:277-283: `__half2float(__hadd(...))`-style adds), so the image tolerance is fp16's."""
+    img, Ts, fi = fwd()
+    assert (fi == refout["nd_final_idx"]).mean() > 0.999, (who, "nd final_idx")
+    same = fi == refout["nd_final_idx"]
+    assert np.abs(Ts[same] - refout["nd_final_Ts"][same]).max() < 2e-5, (who, "nd final_Ts")
+    assert np.abs(img[same] - refout["nd_img"][same]).max() < 2e-2, (who, "nd image", np.abs(img[same] - refout["nd_img"][same]).max())
+    g = bwd()
+    for k in ("v_xy", "v_xy_abs", "v_conic", "v_colors", "v_opacity"):
+        r = refout["nd_" + k]
+        assert _rel(g[k].reshape(r.shape), r) < 2e-2, (who, "nd " + k, _rel(g[k].reshape(r.shape), r))
+
+
+def _oracle_nd_checks(refout, d):
+    nd = _nd_inputs(d)
+    opac = (d["opacity"][:, 0] * refout["compensation"])[:, None].astype(np.float32)
+    common = (d["H"], d["W"], 16, refout["gaussian_ids_sorted"], refout["tile_bins"], refout["xys"], refout["conics"],
+              nd["nd_colors"], opac, nd["nd_background"])
+    fwd = lambda: O.nd_rasterize_forward(*common)
+    bwd = lambda: O.nd_rasterize_backward(*common, refout["nd_final_Ts"], refout["nd_final_idx"], nd["nd_v_out"], nd["nd_v_alpha"])
+    _nd_check(refout, d, "oracle", fwd, bwd)
+
+
+def _product_nd_checks(refout, d):
+    import gsplat.cuda as _C
+
+    H, W = d["H"], d["W"]
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    nd = _nd_inputs(d)
+    opac = cu((d["opacity"][:, 0] * refout["compensation"])[:, None].astype(np.float32))
+    args = (cu(refout["gaussian_ids_sorted"]), cu(refout["tile_bins"]), cu(refout["xys"]), cu(refout["pix_vels"]), 0.0, 0.0,
+            cu(refout["conics"]), cu(nd["nd_colors"]), opac, cu(nd["nd_background"]))
+    fwd = lambda: [t.cpu().numpy() for t in _C.nd_rasterize_forward(tb, (16, 16, 1), (W, H, 1), 1, *args)]
+
+    def bwd():
+        o = _C.nd_rasterize_backward(H, W, 16, 1, *args, cu(refout["nd_final_Ts"]), cu(refout["nd_final_idx"]),
+                                     cu(nd["nd_v_out"]), cu(nd["nd_v_alpha"]))
+        return {k: o[i].cpu().numpy() for k, i in (("v_xy", 0), ("v_xy_abs", 1), ("v_conic", 3), ("v_colors", 4), ("v_opacity", 5))}
+
+    _nd_check(refout, d, "libb200splat", fwd, bwd)
+
+
 def _rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
@@ -186,11 +257,16 @@ def test_reference_cuda_live(tag):
     ref = build_ref.load_ref()
     d = _case(tag)
     refout = _run_reference_cuda(ref, d)
+    if tag == "static":  # the N-channel kernels reject blur / rolling shutter (bindings.cu:541-546)
+        refout.update(_run_reference_cuda_nd(ref, d, refout))
     if os.environ.get("B200_WRITE_REFCUDA"):
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"refcuda_{tag}.npz"), **refout)
     _oracle_checks(refout, d)
     _product_checks(refout, d)
+    if tag == "static":
+        _oracle_nd_checks(refout, d)
+        _product_nd_checks(refout, d)
 
 
 def _fixture(tag):
@@ -203,10 +279,16 @@ def _fixture(tag):
 @pytest.mark.parametrize("tag", list(CASES))
 def test_refcuda_fixture_vs_oracle(tag):
     """CPU: the oracle reproduces the committed reference-CUDA outputs."""
-    _oracle_checks(_fixture(tag), _case(tag))
+    f = _fixture(tag)
+    _oracle_checks(f, _case(tag))
+    if "nd_img" in f:
+        _oracle_nd_checks(f, _case(tag))
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", list(CASES))
 def test_refcuda_fixture_vs_product(tag):
-    _product_checks(_fixture(tag), _case(tag))
+    f = _fixture(tag)
+    _product_checks(f, _case(tag))
+    if "nd_img" in f:
+        _product_nd_checks(f, _case(tag))

@@ -61,3 +61,37 @@ def cu(a, dtype=None):
 def frac_mismatch(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float((a != b).mean())
+
+
+def _np(a):
+    return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+
+
+def close(a, b, atol, rtol, name="", outliers=0.0, outlier_atol=None):
+    """Elementwise |a-b| <= atol + rtol|b|, except for at most a fraction `outliers` of the elements, which must
+    still be within `outlier_atol`.  Outliers exist because the blend has hard thresholds (alpha < 1/255,
+    T <= 1e-4): a 1-ulp difference flips one contribution of size <= 1/255 * T for ~1e-4 of the pixel-samples."""
+    a, b = _np(a).astype(np.float64), _np(b).astype(np.float64)
+    diff = np.abs(a - b)
+    bad = diff > (atol + rtol * np.abs(b))
+    frac = float(bad.mean()) if bad.size else 0.0
+    assert frac <= outliers, f"{name}: {int(bad.sum())} / {bad.size} out of tol (allowed {outliers:g}), max abs diff {diff.max():.3e}"
+    if outlier_atol is not None and bad.any():
+        assert diff.max() <= outlier_atol, f"{name}: outlier {diff.max():.3e} > {outlier_atol:g}"
+
+
+def grad_close(a, b, tol=1e-3, name="", rtol=5e-3, outliers=2e-4):
+    """fp32 atomics / FMA order vs the fp64-accumulating oracle: every element within rtol*|b| + tol*max|b|, up to a
+    fraction `outliers` (threshold flips, see close()); and the tensors as a whole agree to 1e-5 in cosine."""
+    a, b = _np(a).astype(np.float64), _np(b).astype(np.float64)
+    a = a.reshape(b.shape)
+    if np.abs(b).max() == 0.0:  # e.g. v_pix_vels of a static render
+        assert np.abs(a).max() == 0.0, f"{name}: reference gradient is exactly zero, got {np.abs(a).max():.3e}"
+        return
+    scale = max(np.abs(b).max(), 1e-30)
+    diff = np.abs(a - b)
+    bad = diff > (rtol * np.abs(b) + tol * scale)
+    frac = float(bad.mean())
+    assert frac <= outliers, f"{name}: {int(bad.sum())} / {bad.size} out of tol, worst {diff.max() / scale:.3e} of max |ref| {scale:.3e}"
+    cos = float((a * b).sum() / max(np.sqrt((a * a).sum() * (b * b).sum()), 1e-300))
+    assert cos > 1 - 1e-5, f"{name}: cosine {cos}"

@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--what", default="fwd,bwd")
     ap.add_argument("--full", action="store_true", help="blend the reference's full tile lists instead of the culled ones")
+    ap.add_argument("--counters", action="store_true",
+                    help="needs a -DB200_BLEND_COUNTERS build (B200SPLAT_LIB=.../libb200splat_cnt.so): print what one forward and "
+                         "one backward launch execute (entries tested, warp visits, sample blocks, evaluations, useful evaluations)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     sc = synthetic.make_scene(a.config, device=dev, n_override=a.n)
@@ -51,6 +54,26 @@ def main():
     ln = (bins[:, 1] - bins[:, 0]).float()
     print(f"config {a.config}: N={N} I={I} list entries={gids_s.numel()} ({'full' if a.full else 'culled'}) visible={int((nth > 0).sum())} "
           f"tiles={bins.shape[0]} list len mean/max {ln.mean():.0f}/{ln.max():.0f}")
+    if a.counters:
+        import ctypes
+        import json
+
+        from gsplat import _lib
+        lib = _lib.load()
+        buf = (ctypes.c_ulonglong * 16)()
+        lib.b200_blend_counters(None, 1)
+        fwd()
+        bwd()
+        lib.b200_blend_counters(buf, 0)
+        names = ["entries_tested_by_a_warp", "warp_visits", "sample_blocks", "pixel_sample_evaluations",
+                 "evaluations_passing_the_alpha_test", "visits_that_blend_or_reduce"]
+        out = {"config": a.config, "lists": "full" if a.full else "culled", "list_entries": int(gids_s.numel()),
+               "forward": dict(zip(names, [int(x) for x in buf[0:6]])), "backward": dict(zip(names, [int(x) for x in buf[8:14]]))}
+        for k in ("forward", "backward"):
+            d = out[k]
+            d["useful_fraction_of_evaluations"] = round(d["evaluations_passing_the_alpha_test"] / max(1, d["pixel_sample_evaluations"]), 4)
+        print(json.dumps(out))
+        return
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         if name not in a.what.split(","):
             continue
