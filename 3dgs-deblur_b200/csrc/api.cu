@@ -31,6 +31,10 @@ int blend_pixels_per_lane(bool backward) {
     static const int bwd = [] { const char *e = getenv("B200_BLEND_PPL_BWD"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : 2; }();
     return backward ? bwd : fwd;
 }
+bool blend_packed() {
+    static const bool on = [] { const char *e = getenv("B200_BLEND_PACKED"); return !(e && e[0] == '0'); }();
+    return on;
+}
 }  // namespace b200
 #ifdef B200_BLEND_COUNTERS
 namespace b200 { __device__ unsigned long long g_blend_counters[16]; }

@@ -270,11 +270,231 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
     B200_COUNT_FLUSH(8);
 }
 
+
+// ---- two pixels per lane, packed (PPL = 2, 16x16 tiles): the kernel the train step runs ------------------------------
+// Same walk, staging, cull and reduction as blend_backward_kernel<S, 2>; the lane's two pixels (rows r and r + 4 of the
+// warp's 8x8 block) live in the two halves of packed float pairs (f2, blend_common.cuh), so every FMA-pipe instruction of
+// the sigma evaluation and of the gradient algebra issues once for both.  Per-sample structure:
+//   * warp-uniform skips first: the exact cull's sample bit and idx <= (warp max of that sample's last contributor);
+//   * sigma, exp, alpha for both pixels in straight-line code; pixels that fail a test are masked by zeroing `vis` and
+//     `alpha` (then fac, v_sigma and every accumulated term are exactly 0 and T is kept by a select) -- one vote decides
+//     whether the gradient algebra runs at all.
+template <int S>
+__global__ void __launch_bounds__(128, 5) blend_backward_kernel2(const BlendBwdParams p) {
+    constexpr int NT = 128;
+    __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
+    __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
+    __shared__ int s_max[NT / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % p.g.tbx, tile_y = tile / p.g.tbx;
+    const int2 range = p.tile_bins[tile];
+    const float inv_s = 1.0f / (float)S;
+    const float bg0 = __ldg(p.background), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
+
+    bool inside[2];
+    float px[2], py[2], roll[2];
+    float vo[2][3];
+    float Tm_[2][S], D_[2][S];
+    int bin_final[2][S];
+    int smax[S];  // per-sample last contributor over the lane's pixels, then over the warp
+#pragma unroll
+    for (int s = 0; s < S; ++s) smax[s] = -1;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int lx, ly;
+        bool has_pixel;
+        tile_pixel_ppl<2>(p.g.bw, tid, q, lx, ly, has_pixel);
+        const int j = tile_x * p.g.bw + lx, i = tile_y * p.g.bw + ly;
+        inside[q] = has_pixel && i < p.g.H && j < p.g.W;
+        px[q] = (float)j + 0.5f; py[q] = (float)i + 0.5f;
+        roll[q] = (float)((double)p.g.rs_time * ((double)(py[q] / (float)p.g.H) - 0.5));
+        const size_t pix = inside[q] ? (size_t)i * p.g.W + j : 0;
+        float voa = 0.f;
+        vo[q][0] = vo[q][1] = vo[q][2] = 0.f;
+        if (inside[q]) {
+            vo[q][0] = p.v_out[3 * pix]; vo[q][1] = p.v_out[3 * pix + 1]; vo[q][2] = p.v_out[3 * pix + 2];
+            voa = p.v_out_alpha ? p.v_out_alpha[pix] : 0.f;
+        }
+        const float bgdot = bg0 * vo[q][0] + bg1 * vo[q][1] + bg2 * vo[q][2];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            Tm_[q][s] = inv_s; D_[q][s] = 0.f; bin_final[q][s] = -1;
+            if (inside[q]) {
+                const float Tf = p.final_Ts[pix * S + s];
+                Tm_[q][s] = Tf * inv_s;
+                D_[q][s] = Tf * inv_s * (voa - bgdot);
+                bin_final[q][s] = min(p.final_idx[pix * S + s], range.y - 1);
+                smax[s] = max(smax[s], bin_final[q][s]);
+            }
+        }
+    }
+    const WarpWindow win = warp_window<2>(inside, px, py, roll);
+    int wmax = -1;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        smax[s] = __reduce_max_sync(0xffffffffu, smax[s]);
+        wmax = max(wmax, smax[s]);
+    }
+    if (lane == 0) s_max[warp] = wmax;
+    // packed per-pixel state
+    f2 Tm[S], D[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { Tm[s] = f2_make(Tm_[0][s], Tm_[1][s]); D[s] = f2_make(D_[0][s], D_[1][s]); }
+    const f2 PX = f2_make(px[0], px[1]), PY = f2_make(py[0], py[1]), ROLL = f2_make(roll[0], roll[1]);
+    const f2 VO0 = f2_make(vo[0][0], vo[1][0]), VO1 = f2_make(vo[0][1], vo[1][1]), VO2 = f2_make(vo[0][2], vo[1][2]);
+    float blur[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) blur[s] = blur_offset<S>(s, p.g.exposure);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < BLEND_STAGES; ++st) mbar_init(&s_bar[st], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    int hi = -1;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) hi = max(hi, s_max[w]);
+    const int total = hi - range.x + 1;
+    const int nb = total > 0 ? (total + BLEND_BATCH - 1) / BLEND_BATCH : 0;
+
+    float *my_dst = nullptr;
+    int my_stride = 0;
+    {
+        const int k = lane >> 1;
+        if ((lane & 1) == 0) {
+            if (k < 3) { my_dst = p.v_rgb + k; my_stride = 3; }
+            else if (k < 6) { my_dst = p.v_conic + (k - 3); my_stride = 3; }
+            else if (k < 8) { my_dst = p.v_xy + (k - 6); my_stride = 2; }
+            else if (k < 10) { my_dst = p.v_xy_abs + (k - 8); my_stride = 2; }
+            else if (k < 12) { my_dst = p.v_pix_vel + (k - 10); my_stride = 2; }
+            else if (k == 12) { my_dst = p.v_opac; my_stride = 1; }
+        }
+    }
+
+    auto issue = [&](int b) {
+        const int st = b & 1;
+        const int top = hi - b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, top - range.x + 1);
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], (uint32_t)cnt * (uint32_t)sizeof(PackedGaussian));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int e = tid + r * NT;
+            if (e < cnt) {
+                const int g = __ldg(p.ids_sorted + top - e);
+                tma_bulk_g2s(&s_rec[st][e], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+            }
+        }
+    };
+
+    B200_COUNT_DECL;
+    if (nb > 0) issue(0);
+    for (int b = 0; b < nb; ++b) {
+        const int st = b & 1;
+        if (b + 1 < nb) issue(b + 1);
+        mbar_wait(&s_bar[st], (uint32_t)((b >> 1) & 1));
+        const int top = hi - b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, top - range.x + 1);
+
+        if (wmax >= range.x) {
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                const int e = c0 + lane;
+                const unsigned my_mask =
+                    ((e < cnt) && (top - e <= wmax)) ? sample_mask_exact<S>(s_rec[st][e], win, p.g.exposure) : 0u;
+                unsigned m = __ballot_sync(0xffffffffu, my_mask != 0u);
+                if ((e < cnt) && (top - e <= wmax)) B200_COUNT(0, 1);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    const int k = c0 + src;
+                    m &= m - 1;
+                    const unsigned smask = __shfl_sync(0xffffffffu, my_mask, src);
+                    if (lane == 0) { B200_COUNT(1, 1); B200_COUNT(2, __popc(smask)); }
+                    const int idx = top - k;
+                    const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
+                    const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
+                    const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
+                    const float cut = C.w + 1e-4f;
+                    const f2 VX = f2_splat(A.z), VY = f2_splat(A.w);
+                    const f2 CA = f2_splat(Bq.x), CB = f2_splat(Bq.y), CC = f2_splat(Bq.z);
+                    const f2 HA = f2_splat(0.5f * Bq.x), HC = f2_splat(0.5f * Bq.z), OP = f2_splat(Bq.w);
+                    const f2 dx0 = f2_sub(f2_splat(A.x), PX), dy0 = f2_sub(f2_splat(A.y), PY);
+                    const f2 cdot = f2_fma(f2_splat(C.x), VO0, f2_fma(f2_splat(C.y), VO1, f2_mul(f2_splat(C.z), VO2)));
+                    const f2 zero = f2_splat(0.f);
+                    f2 sxx = zero, sxy = zero, syy = zero, gxs = zero, gys = zero, pvx = zero, pvy = zero, vop = zero, facsum = zero;
+                    float gxa = 0.f, gya = 0.f;
+                    bool any = false;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (!(smask & (1u << s)) || idx > smax[s]) continue;  // warp-uniform
+                        const f2 tau = f2_add(f2_splat(blur[s]), ROLL);
+                        const f2 dx = f2_fma(tau, VX, dx0), dy = f2_fma(tau, VY, dy0);
+                        const f2 u0 = f2_fma(HA, dx, f2_mul(CB, dy));
+                        const f2 sigma = f2_fma(dx, u0, f2_mul(f2_mul(HC, dy), dy));
+                        const float sg0 = f2_lo(sigma), sg1 = f2_hi(sigma);
+                        bool ok0 = (idx <= bin_final[0][s]) && !(sg0 > cut || sg0 < 0.f);  // backward.cu:252-254,276
+                        bool ok1 = (idx <= bin_final[1][s]) && !(sg1 > cut || sg1 < 0.f);
+                        if (inside[0]) B200_COUNT(3, 1);
+                        if (inside[1]) B200_COUNT(3, 1);
+                        // exp(-sigma): masked pixels evaluate exp(0)
+                        float v0 = exp_neg_approx(ok0 ? sg0 : 0.f), v1 = exp_neg_approx(ok1 ? sg1 : 0.f);
+                        float a0 = fminf(0.99f, Bq.w * v0), a1 = fminf(0.99f, Bq.w * v1);
+                        ok0 = ok0 && !(a0 < 1.f / 255.f);
+                        ok1 = ok1 && !(a1 < 1.f / 255.f);
+                        if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+                        any = true;
+                        if (ok0) B200_COUNT(4, 1);
+                        if (ok1) B200_COUNT(4, 1);
+                        // masked pixels: vis = alpha = 0  =>  ra = 1, fac = 0, v_sigma = 0, every accumulated term exactly 0
+                        const f2 vis = f2_make(ok0 ? v0 : 0.f, ok1 ? v1 : 0.f);
+                        const f2 alpha = f2_make(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
+                        const f2 ov = f2_mul(OP, vis);
+                        const f2 om = f2_sub(f2_splat(1.f), alpha);
+                        const f2 ra = f2_make(rcp_approx(f2_lo(om)), rcp_approx(f2_hi(om)));
+                        const f2 Tn = f2_mul(Tm[s], ra);                 // T / S of backward.cu:294-296
+                        const f2 fac = f2_mul(alpha, Tn);
+                        const f2 v_alpha = f2_fma(Tn, cdot, f2_mul(ra, D[s]));  // backward.cu:303-311
+                        // no zeroing when the clamp is active (backward.cu:317)
+                        const f2 v_sigma = f2_mul(f2_sub(zero, ov), v_alpha);
+                        Tm[s] = f2_make(ok0 ? f2_lo(Tn) : f2_lo(Tm[s]), ok1 ? f2_hi(Tn) : f2_hi(Tm[s]));
+                        D[s] = f2_fma(f2_sub(zero, fac), cdot, D[s]);     // running buffer, :313-315
+                        facsum = f2_add(facsum, fac);
+                        const f2 u = f2_mul(v_sigma, dx), w = f2_mul(v_sigma, dy);
+                        sxx = f2_fma(u, dx, sxx); sxy = f2_fma(u, dy, sxy); syy = f2_fma(w, dy, syy);
+                        const f2 gx = f2_fma(CA, u, f2_mul(CB, w));
+                        const f2 gy = f2_fma(CB, u, f2_mul(CC, w));
+                        gxs = f2_add(gxs, gx); gys = f2_add(gys, gy);
+                        gxa += fabsf(f2_lo(gx)); gxa += fabsf(f2_hi(gx));
+                        gya += fabsf(f2_lo(gy)); gya += fabsf(f2_hi(gy));
+                        pvx = f2_fma(gx, tau, pvx); pvy = f2_fma(gy, tau, pvy);
+                        vop = f2_fma(vis, v_alpha, vop);
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
+                    if (lane == 0) B200_COUNT(5, 1);
+                    const float v[16] = {f2_sum(f2_mul(facsum, VO0)), f2_sum(f2_mul(facsum, VO1)), f2_sum(f2_mul(facsum, VO2)),
+                                         0.5f * f2_sum(sxx), f2_sum(sxy), 0.5f * f2_sum(syy), f2_sum(gxs), f2_sum(gys), gxa, gya,
+                                         f2_sum(pvx), f2_sum(pvy), f2_sum(vop), 0.f, 0.f, 0.f};
+                    const float tot = butterfly16(v, lane);
+                    if (my_dst && tot != 0.f) {
+                        const int gid = s_rec[st][k].id;
+                        atomicAdd(my_dst + (unsigned)gid * (unsigned)my_stride, tot);  // N * 3 < 2^32
+                    }
+                }
+            }
+        }
+        __syncthreads();  // stage `st` is refilled two batches from now
+    }
+    B200_COUNT_FLUSH(8);
+}
+
 template <int S>
 static int launch_bwd(const BlendBwdParams &p, cudaStream_t st) {
     if (p.g.bw == 16 && blend_pixels_per_lane(true) == 4)  // experimental (B200_BLEND_PPL_BWD=4)
         blend_backward_kernel<S, 4><<<p.g.tbx * p.g.tby, BLEND_THREADS / 4, 0, st>>>(p);
-    else if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2)
+    else if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2 && blend_packed())
+        blend_backward_kernel2<S><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
+    else if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2)  // B200_BLEND_PACKED=0: the scalar two-pixel kernel (A/B)
         blend_backward_kernel<S, 2><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
     else
         blend_backward_kernel<S, 1><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);

@@ -11,6 +11,8 @@ constexpr int BLEND_STAGES = 2;
 // 1 or 2 pixels per lane in the blend kernels (B200_BLEND_PPL_FWD / B200_BLEND_PPL_BWD, default 2; only
 // 16x16 tiles can use 2)
 int blend_pixels_per_lane(bool backward);
+// two-pixel kernels: packed f32x2 form (default) or the scalar form (B200_BLEND_PACKED=0)
+bool blend_packed();
 
 // -DB200_BLEND_COUNTERS (A/B build only, see tools/blend_counters.py): the blend kernels count what they execute --
 //   [0] tile-list entries tested by a warp cull   [1] warp visits (entries that survive it)
@@ -184,6 +186,54 @@ __device__ __forceinline__ WarpWindow warp_window(const bool (&live)[PPL], const
     return w;
 }
 
+// ---- two pixels per lane as ONE packed float pair ---------------------------------------------------------------
+// sm_100a has packed fp32 arithmetic: fma/mul/add.rn.f32x2 (SASS FFMA2 / FMUL2 / FADD2) work on a 64-bit register pair,
+// each half rounded exactly like the scalar instruction.  The FMA pipe is busy two cycles per packed instruction, so a
+// loop bound by that pipe gains nothing (tools/micro/ffma2_bench.cu) -- but the blend kernels are bound by instruction
+// ISSUE with the FMA pipe ~42 % busy, and a lane's two pixels run identical instruction streams: one issue slot instead
+// of two for every FMA-pipe instruction (tools/micro/ffma2_mix_bench.cu measures the mix).  ALU-pipe work (compares,
+// selects, min/max) and the MUFU calls address the two halves as ordinary 32-bit registers, no moves needed.
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 f2_splat(float x) { return f2_make(x, x); }
+__device__ __forceinline__ float f2_lo(f2 x) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v));
+    return a;
+}
+__device__ __forceinline__ float f2_hi(f2 x) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v));
+    return b;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ float f2_sum(f2 x) { return f2_lo(x) + f2_hi(x); }
+
 // sigma of forward.cu:405-410 / backward.cu:263-268 for one pixel and one blur sample.
 // The pixel-independent parts are hoisted per tile-list entry (half conics) and per pixel (offset at tau = 0) and the
 // quadratic form is evaluated as dx * (a/2 dx + b dy) + c/2 dy^2; -DB200_SIGMA_FACTORED=0 compiles the reference's
@@ -253,23 +303,19 @@ __device__ __forceinline__ unsigned sample_mask(const PackedGaussian &g, const W
 #ifndef B200_EXACT_CULL
 #define B200_EXACT_CULL 1
 #endif
-__device__ __forceinline__ bool box_may_reach(float a, float b, float c, float inv_a, float inv_c, float thr, float x0,
+__device__ __forceinline__ bool box_may_reach(float a, float b, float c, float nb_inv_a, float nb_inv_c, float thr, float x0,
                                               float x1, float y0, float y1) {
-    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;
-    float best = __int_as_float(0x7f800000);
-    {
-        const float t0 = fminf(fmaxf(-b * x0 * inv_c, y0), y1), t1 = fminf(fmaxf(-b * x1 * inv_c, y0), y1);
-        best = fminf(best, 0.5f * (a * x0 * x0 + c * t0 * t0) + b * x0 * t0);
-        best = fminf(best, 0.5f * (a * x1 * x1 + c * t1 * t1) + b * x1 * t1);
-    }
-    {
-        const float t0 = fminf(fmaxf(-b * y0 * inv_a, x0), x1), t1 = fminf(fmaxf(-b * y1 * inv_a, x0), x1);
-        best = fminf(best, 0.5f * (a * t0 * t0 + c * y0 * y0) + b * t0 * y0);
-        best = fminf(best, 0.5f * (a * t1 * t1 + c * y1 * y1) + b * t1 * y1);
-    }
+    // the edges of the box that face the origin (if the box straddles an axis either edge of that pair serves: the
+    // minimum then lies on the facing edge of the OTHER pair, which is evaluated as well)
+    const float X = x0 > 0.f ? x0 : x1, Y = y0 > 0.f ? y0 : y1;
+    const bool inside = (x0 <= 0.f) & (x1 >= 0.f) & (y0 <= 0.f) & (y1 >= 0.f);
+    const float ty = fminf(fmaxf(nb_inv_c * X, y0), y1);  // argmin over dy of sigma(X, dy) = -b X / c, clamped to the edge
+    const float tx = fminf(fmaxf(nb_inv_a * Y, x0), x1);
+    const float s1 = 0.5f * (a * X * X + c * ty * ty) + b * X * ty;
+    const float s2 = 0.5f * (a * tx * tx + c * Y * Y) + b * tx * Y;
     const float mx = fmaxf(fabsf(x0), fabsf(x1)), my = fmaxf(fabsf(y0), fabsf(y1));
     const float mag = 0.5f * (a * mx * mx + c * my * my) + fabsf(b) * mx * my;
-    return !(best > thr + (2e-5f * mag + 1e-3f));
+    return inside | !(fminf(s1, s2) > thr + (2e-5f * mag + 1e-3f));
 }
 
 // sample_mask + the exact refinement for the surviving samples (bounded, positive-definite conics only: the record
@@ -279,18 +325,19 @@ __device__ __forceinline__ unsigned sample_mask_exact(const PackedGaussian &g, c
     unsigned m = sample_mask<S>(g, w, exposure);
 #if B200_EXACT_CULL
     if (m == 0u || !(g.hx < 3.0e38f)) return m;
-    const float inv_a = 1.0f / g.ca, inv_c = 1.0f / g.cc;
+    // -b/a, -b/c: the clamped vertex only has to be near the minimiser (sigma is flat to second order there)
+    const float nb_inv_a = -g.cb * rcp_approx(g.ca), nb_inv_c = -g.cb * rcp_approx(g.cc);
+    // (the box corners below are rounded differences: widen by a hair so the box contains every evaluated offset)
+    const float ex = 1e-6f * (fabsf(g.x) + fabsf(w.x0) + fabsf(w.x1)) + 1e-4f, ey = 1e-6f * (fabsf(g.y) + fabsf(w.y0) + fabsf(w.y1)) + 1e-4f;
+    const float bx0 = (g.x - w.x1) - ex, bx1 = (g.x - w.x0) + ex, by0 = (g.y - w.y1) - ey, by1 = (g.y - w.y0) + ey;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        if (!(m & (1u << s))) continue;
         const float b = blur_offset<S>(s, exposure);
         const float t0 = b + w.r0, t1 = b + w.r1;
         const float ax = t0 * g.vx, bx = t1 * g.vx, ay = t0 * g.vy, by = t1 * g.vy;
-        const float x0 = (g.x + fminf(ax, bx)) - w.x1, x1 = (g.x + fmaxf(ax, bx)) - w.x0;
-        const float y0 = (g.y + fminf(ay, by)) - w.y1, y1 = (g.y + fmaxf(ay, by)) - w.y0;
-        // (the differences above are rounded: widen the box by a hair so it still contains every evaluated offset)
-        const float ex = 1e-6f * (fabsf(g.x) + fabsf(w.x0) + fabsf(w.x1)) + 1e-4f, ey = 1e-6f * (fabsf(g.y) + fabsf(w.y0) + fabsf(w.y1)) + 1e-4f;
-        if (!box_may_reach(g.ca, g.cb, g.cc, inv_a, inv_c, g.thr, x0 - ex, x1 + ex, y0 - ey, y1 + ey)) m &= ~(1u << s);
+        const bool keep = box_may_reach(g.ca, g.cb, g.cc, nb_inv_a, nb_inv_c, g.thr, bx0 + fminf(ax, bx), bx1 + fmaxf(ax, bx),
+                                        by0 + fminf(ay, by), by1 + fmaxf(ay, by));
+        if (!keep) m &= ~(1u << s);
     }
 #endif
     return m;

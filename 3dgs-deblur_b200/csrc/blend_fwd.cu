@@ -28,7 +28,7 @@ struct BlendFwdParams {
 };
 
 template <int S, int PPL>
-__global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(const BlendFwdParams p) {
+__global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 6 : 1) blend_forward_kernel(const BlendFwdParams p) {
     constexpr int NT = BLEND_THREADS / PPL;  // threads per tile
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
@@ -196,12 +196,203 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL) blend_forward_kernel(cons
     }
 }
 
+
+// ---- two pixels per lane, packed (PPL = 2, 16x16 tiles): the kernel the train step runs ------------------------------
+// Same walk, staging and cull as blend_forward_kernel<S, 2>.  The lane's two pixels live in the halves of packed float
+// pairs (f2, blend_common.cuh) and are evaluated side by side in straight-line code: the sigma quadratic, alpha * T and the
+// three colour accumulations issue once for both pixels (FFMA2 / FMUL2 / FADD2), failed tests mask instead of branching
+// (alpha = 0 leaves T, the colour sums and `last` untouched), and one warp vote per sample skips the blend arithmetic
+// when no lane passes.  The branchy one-pixel-at-a-time form costs ~32 issue slots per pixel-sample, this ~23.
+template <int S>
+__global__ void __launch_bounds__(128, 6) blend_forward_kernel2(const BlendFwdParams p) {
+    constexpr int NT = 128;
+    __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
+    __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % p.g.tbx, tile_y = tile / p.g.tbx;
+    bool inside[2];
+    float px[2], py[2], roll[2];
+    int pi[2], pj[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int lx, ly;
+        bool has_pixel;
+        tile_pixel_ppl<2>(p.g.bw, tid, q, lx, ly, has_pixel);
+        pj[q] = tile_x * p.g.bw + lx; pi[q] = tile_y * p.g.bw + ly;
+        inside[q] = has_pixel && pi[q] < p.g.H && pj[q] < p.g.W;
+        px[q] = (float)pj[q] + 0.5f; py[q] = (float)pi[q] + 0.5f;
+        roll[q] = (float)((double)p.g.rs_time * ((double)(py[q] / (float)p.g.H) - 0.5));  // forward.cu:360
+    }
+    float blur[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) blur[s] = blur_offset<S>(s, p.g.exposure);
+    const WarpWindow win = warp_window<2>(inside, px, py, roll);
+    const f2 PX = f2_make(px[0], px[1]), PY = f2_make(py[0], py[1]), ROLL = f2_make(roll[0], roll[1]);
+
+    const int2 range = p.tile_bins[tile];
+    const int total = range.y - range.x;
+    const int nb = (total + BLEND_BATCH - 1) / BLEND_BATCH;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < BLEND_STAGES; ++st) mbar_init(&s_bar[st], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int b) {
+        const int st = b & 1;
+        const int start = range.x + b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, range.y - start);
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], (uint32_t)cnt * (uint32_t)sizeof(PackedGaussian));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int e = tid + r * NT;
+            if (e < cnt) {
+                const int g = __ldg(p.ids_sorted + start + e);
+                tma_bulk_g2s(&s_rec[st][e], p.packed + g, (uint32_t)sizeof(PackedGaussian), &s_bar[st]);
+            }
+        }
+    };
+
+    const float inv_s = 1.0f / (float)S;
+    f2 T[S];
+    int last[2][S];
+    f2 acc0 = f2_splat(0.f), acc1 = f2_splat(0.f), acc2 = f2_splat(0.f);
+    unsigned alive[2];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { T[s] = f2_splat(1.f); last[0][s] = 0; last[1][s] = 0; }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) alive[q] = inside[q] ? ((1u << S) - 1u) : 0u;
+    unsigned walive = __reduce_or_sync(0xffffffffu, alive[0] | alive[1]);  // samples some lane of the warp still blends
+
+    B200_COUNT_DECL;
+    int b = 0;
+    bool pending = false;
+    if (nb > 0) { issue(0); pending = true; }
+    for (; b < nb; ++b) {
+        const int st = b & 1;
+        if (b + 1 < nb) issue(b + 1);
+        mbar_wait(&s_bar[st], (uint32_t)((b >> 1) & 1));
+        pending = (b + 1 < nb);
+        const int start = range.x + b * BLEND_BATCH;
+        const int cnt = min(BLEND_BATCH, range.y - start);
+
+        if (walive) {
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                const int e = c0 + lane;
+                const unsigned my_mask = (e < cnt) ? sample_mask_exact<S>(s_rec[st][e], win, p.g.exposure) : 0u;
+                unsigned m = __ballot_sync(0xffffffffu, my_mask != 0u);
+                if (e < cnt) B200_COUNT(0, 1);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    const int k = c0 + src;
+                    m &= m - 1;
+                    const unsigned smask = __shfl_sync(0xffffffffu, my_mask, src) & walive;
+                    if (smask == 0u) continue;
+                    if (lane == 0) { B200_COUNT(1, 1); B200_COUNT(2, __popc(smask)); }
+                    const float4 A = *reinterpret_cast<const float4 *>(&s_rec[st][k].x);    // x y vx vy
+                    const float4 Bq = *reinterpret_cast<const float4 *>(&s_rec[st][k].ca);  // a b c opac
+                    const float4 C = *reinterpret_cast<const float4 *>(&s_rec[st][k].r);    // r g b thr
+                    const float cut = C.w + 1e-4f;
+                    const f2 VX = f2_splat(A.z), VY = f2_splat(A.w);
+                    const f2 CBq = f2_splat(Bq.y), HA = f2_splat(0.5f * Bq.x), HC = f2_splat(0.5f * Bq.z), OP = f2_splat(Bq.w);
+                    const f2 CR = f2_splat(C.x * inv_s), CG = f2_splat(C.y * inv_s), CBl = f2_splat(C.z * inv_s);
+                    const f2 dx0 = f2_sub(f2_splat(A.x), PX), dy0 = f2_sub(f2_splat(A.y), PY);
+                    const int idx = start + k;
+                    const unsigned alive_before = alive[0] + alive[1];
+#ifdef B200_BLEND_COUNTERS
+                    bool blended_ = false;
+#endif
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (!(smask & (1u << s))) continue;  // warp-uniform
+                        const f2 tau = f2_add(f2_splat(blur[s]), ROLL);
+                        const f2 dx = f2_fma(tau, VX, dx0), dy = f2_fma(tau, VY, dy0);
+                        const f2 u0 = f2_fma(HA, dx, f2_mul(CBq, dy));
+                        const f2 sigma = f2_fma(dx, u0, f2_mul(f2_mul(HC, dy), dy));
+                        const float sg0 = f2_lo(sigma), sg1 = f2_hi(sigma);
+                        bool ok0 = (alive[0] & (1u << s)) != 0u, ok1 = (alive[1] & (1u << s)) != 0u;
+                        if (ok0) B200_COUNT(3, 1);
+                        if (ok1) B200_COUNT(3, 1);
+                        ok0 = ok0 && !(sg0 > cut || sg0 < 0.f);  // alpha < 1/255 guaranteed above thr (NaN passes, as in the reference)
+                        ok1 = ok1 && !(sg1 > cut || sg1 < 0.f);
+                        const f2 ex = f2_mul(sigma, f2_splat(-1.4426950408889634f));
+                        float v0, v1;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v0) : "f"(f2_lo(ex)));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v1) : "f"(f2_hi(ex)));
+                        const f2 ov = f2_mul(OP, f2_make(v0, v1));
+                        const float a0 = fminf(0.999f, f2_lo(ov)), a1 = fminf(0.999f, f2_hi(ov));
+                        ok0 = ok0 && !(a0 < 1.f / 255.f);
+                        ok1 = ok1 && !(a1 < 1.f / 255.f);
+                        if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+                        if (ok0) B200_COUNT(4, 1);
+                        if (ok1) B200_COUNT(4, 1);
+#ifdef B200_BLEND_COUNTERS
+                        blended_ = true;
+#endif
+                        const f2 nT = f2_mul(T[s], f2_sub(f2_splat(1.f), f2_make(a0, a1)));
+                        // forward.cu:421-427: T would drop to <= 1e-4: this sample is done for the pixel, entry not blended
+                        const bool stop0 = ok0 && (f2_lo(nT) <= 1e-4f), stop1 = ok1 && (f2_hi(nT) <= 1e-4f);
+                        if (stop0) alive[0] &= ~(1u << s);
+                        if (stop1) alive[1] &= ~(1u << s);
+                        ok0 = ok0 && !stop0;
+                        ok1 = ok1 && !stop1;
+                        const f2 vis = f2_mul(f2_make(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f), T[s]);  // alpha * T (1/S is in the colour)
+                        acc0 = f2_fma(CR, vis, acc0); acc1 = f2_fma(CG, vis, acc1); acc2 = f2_fma(CBl, vis, acc2);
+                        T[s] = f2_make(ok0 ? f2_lo(nT) : f2_lo(T[s]), ok1 ? f2_hi(nT) : f2_hi(T[s]));
+                        last[0][s] = ok0 ? idx : last[0][s];
+                        last[1][s] = ok1 ? idx : last[1][s];
+                    }
+#ifdef B200_BLEND_COUNTERS
+                    if (__any_sync(0xffffffffu, blended_) && lane == 0) B200_COUNT(5, 1);
+#endif
+                    // (bits only ever clear, so the sum of the two masks drops iff one did)
+                    if (__any_sync(0xffffffffu, (alive[0] + alive[1]) != alive_before)) {  // rare: refresh the warp's live set
+                        walive = __reduce_or_sync(0xffffffffu, alive[0] | alive[1]);
+                        if (walive == 0u) { m = 0; c0 = cnt; }
+                    }
+                }
+            }
+        }
+        // all warps are done with stage `st` (it is refilled two batches from now) + early exit vote
+        if (!__syncthreads_or(walive != 0u)) { ++b; break; }
+    }
+    if (pending && b < nb) mbar_wait(&s_bar[b & 1], (uint32_t)((b >> 1) & 1));  // drain the prefetch before exit
+    B200_COUNT_FLUSH(0);
+
+    const float bg0 = __ldg(p.background), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (!inside[q]) continue;
+        const size_t pix = (size_t)pi[q] * p.g.W + pj[q];
+        float meanT = 0.f, sumT = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float Ts = q == 0 ? f2_lo(T[s]) : f2_hi(T[s]);
+            meanT += Ts * inv_s;
+            sumT += Ts;
+            p.final_Ts[pix * S + s] = Ts;
+            p.final_idx[pix * S + s] = last[q][s];
+        }
+        const float r = q == 0 ? f2_lo(acc0) : f2_hi(acc0), g = q == 0 ? f2_lo(acc1) : f2_hi(acc1), bl = q == 0 ? f2_lo(acc2) : f2_hi(acc2);
+        p.out_img[3 * pix] = r + meanT * bg0;
+        p.out_img[3 * pix + 1] = g + meanT * bg1;
+        p.out_img[3 * pix + 2] = bl + meanT * bg2;
+        if (p.out_alpha) p.out_alpha[pix] = 1.0f - sumT * inv_s;
+    }
+}
+
 template <int S>
 static int launch_fwd(const BlendFwdParams &p, cudaStream_t st) {
     // two pixels per lane when the tile is the full 16x16 (the only size Splatfacto uses, splatfacto.py:815)
     if (p.g.bw == 16 && blend_pixels_per_lane(false) == 4)  // experimental (B200_BLEND_PPL_FWD=4)
         blend_forward_kernel<S, 4><<<p.g.tbx * p.g.tby, BLEND_THREADS / 4, 0, st>>>(p);
-    else if (p.g.bw == 16 && blend_pixels_per_lane(false) == 2)
+    else if (p.g.bw == 16 && blend_pixels_per_lane(false) == 2 && blend_packed())
+        blend_forward_kernel2<S><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
+    else if (p.g.bw == 16 && blend_pixels_per_lane(false) == 2)  // B200_BLEND_PACKED=0: the scalar two-pixel kernel (A/B)
         blend_forward_kernel<S, 2><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
     else
         blend_forward_kernel<S, 1><<<p.g.tbx * p.g.tby, BLEND_THREADS, 0, st>>>(p);
