@@ -139,18 +139,21 @@ __global__ void __launch_bounds__(256) emit_tiles_kernel(int n, int num_intersec
     }
 }
 
+// `num_tiles` = first key that is not a tile: the capacity-sized lists of b200_bin_cull_emit_capacity are padded with it
+// (it sorts behind every real entry), and padding entries open / close no range.
 __global__ void __launch_bounds__(256) tile_bin_edges32_kernel(int m, const uint32_t *__restrict__ sorted,
-                                                               int2 *__restrict__ bins) {
+                                                               int2 *__restrict__ bins, int num_tiles) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const int cur = (int)sorted[i];
-    if (i == 0) bins[cur].x = 0;
-    if (i == m - 1) bins[cur].y = m;
+    const bool real = cur < num_tiles;
+    if (i == 0 && real) bins[cur].x = 0;
+    if (i == m - 1 && real) bins[cur].y = m;
     if (i == 0) return;
     const int prev = (int)sorted[i - 1];
     if (prev != cur) {
-        bins[prev].y = i;
-        bins[cur].x = i;
+        bins[prev].y = i;  // (prev < cur: prev is a real tile)
+        if (real) bins[cur].x = i;
     }
 }
 
@@ -349,7 +352,8 @@ __global__ void __launch_bounds__(256, 8) cull_chunks_kernel(int n, int total_en
                                                           int32_t *__restrict__ survivors,             // count pass
                                                           const int32_t *__restrict__ base_of,         // emit pass
                                                           int32_t *__restrict__ cursor, uint32_t *__restrict__ tile_keys,
-                                                          int32_t *__restrict__ ids) {
+                                                          int32_t *__restrict__ ids, uint32_t pad_key,
+                                                          int32_t *__restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -359,6 +363,23 @@ __global__ void __launch_bounds__(256, 8) cull_chunks_kernel(int n, int total_en
         for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < min(phantoms, total_entries); k += gridDim.x * blockDim.x) {
             tile_keys[k] = 0u;
             ids[k] = 0;
+        }
+        if (status) {
+            // capacity mode (b200_bin_cull_emit_capacity): `total_entries` is the caller's list capacity, the real entry
+            // count sits in counters[3].  Pad the tail with a key that sorts behind every tile; report an overflow
+            // (entries beyond the capacity are dropped by the bound checks below: the lists are then incomplete).
+            const int entries = counters[3];
+            for (int k = max(0, min(entries, total_entries)) + blockIdx.x * blockDim.x + threadIdx.x; k < total_entries;
+                 k += gridDim.x * blockDim.x) {
+                tile_keys[k] = pad_key;
+                ids[k] = 0;
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (entries > total_entries) atomicOr(status + 0, 1);
+                status[1] = entries;
+                atomicMax(status + 2, entries);
+                status[3] = counters[0];
+            }
         }
     }
     const int per = (total_chunks + warps - 1) / warps;
@@ -578,7 +599,7 @@ extern "C" int b200_bin_tiles(int num_points, int num_intersects, const float *x
     if (bits < 1) bits = 1;
     B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, tkeys_a, tkeys_b, ids_a, gaussian_ids_sorted, m, 0, bits, st));
     count_launch(1 + (bits + 7) / 8);
-    tile_bin_edges32_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, tkeys_b, reinterpret_cast<int2 *>(tile_bins));
+    tile_bin_edges32_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, tkeys_b, reinterpret_cast<int2 *>(tile_bins), num_tiles);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -687,7 +708,7 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
     B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");
-    B200_REQUIRE(packed && depths && radii && num_tiles_hit && ws_g && totals_host_pinned, "null pointer");
+    B200_REQUIRE(packed && depths && radii && num_tiles_hit && ws_g, "null pointer");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(ws_g) & 255u) == 0, "workspace must be 256-byte aligned");
     const int n = num_points;
     const CullWsG L = cull_ws_g(n);
@@ -726,7 +747,7 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, chunks, chunk_off, n, st));
     count_launch(2);
     (c.per_sample ? cull_chunks_kernel<false, true> : cull_chunks_kernel<false, false>)<<<CULL_GRID, 256, 0, st>>>(
-        n, 0, rec, bbox, chunk_off, chunks, c, counters, masks, L.mask_cap, survivors, nullptr, nullptr, nullptr, nullptr);
+        n, 0, rec, bbox, chunk_off, chunks, c, counters, masks, L.mask_cap, survivors, nullptr, nullptr, nullptr, nullptr, 0u, nullptr);
     B200_LAUNCH_CHECK();
     // (a later record of the shared join event by another caller is ordered after this one on the side stream)
     B200_CUDA(cudaStreamWaitEvent(st, side.join, 0));
@@ -736,7 +757,8 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     count_launch(2);
     cull_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, order, offs, surv_sorted, base_of, counters, flag_dev);
     B200_LAUNCH_CHECK();
-    B200_CUDA(cudaMemcpyAsync(totals_host_pinned, counters, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (totals_host_pinned)  // (null in the capacity mode: nothing on the host waits for the totals)
+        B200_CUDA(cudaMemcpyAsync(totals_host_pinned, counters, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return B200_OK;
 }
 
@@ -773,13 +795,65 @@ extern "C" int b200_bin_cull_emit(int num_points, int num_entries, const void *p
     size_t cub_bytes = E.cub_bytes;
     (c.per_sample ? cull_chunks_kernel<true, true> : cull_chunks_kernel<true, false>)<<<CULL_GRID, 256, 0, st>>>(
         n, m, reinterpret_cast<const PackedGaussian *>(packed), bbox, chunk_off, chunks, c, counters, masks, G.mask_cap, nullptr,
-        base_of, cursor, tkeys_a, ids_a);
+        base_of, cursor, tkeys_a, ids_a, 0u, nullptr);
     B200_LAUNCH_CHECK();
     int bits = key_end_bit(num_tiles) - 32;
     if (bits < 1) bits = 1;
     B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, tkeys_a, tkeys_b, ids_a, gaussian_ids_sorted, m, 0, bits, st));
     count_launch(1 + (bits + 7) / 8);
-    tile_bin_edges32_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, tkeys_b, reinterpret_cast<int2 *>(tile_bins));
+    tile_bin_edges32_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, tkeys_b, reinterpret_cast<int2 *>(tile_bins), num_tiles);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+
+// Capacity mode of the emit phase: the caller sizes the lists from a running high-water mark instead of waiting for this
+// call's entry count, so nothing on the path synchronises with the host (the reference blocks in `.item()`,
+// gsplat/utils.py:123-124, and b200_bin_cull_count + b200_bin_cull_emit block once for the culled count).  The id list
+// has `capacity` slots: the real entries in the reference's order, then padding that belongs to no tile.  status (DEVICE
+// int32[4]): [0] |= 1 if this call's entries did not fit (the lists are then incomplete and the render must be
+// discarded -- the caller vetoes the optimizer step, grows the capacity and repeats the image), [1] = entries of this
+// call, [2] = max(entries seen), [3] = the reference's num_intersects of this call (0 selects its empty-render branch
+// in b200_blend_forward_packed_status).
+extern "C" int b200_bin_cull_emit_capacity(int num_points, int capacity, const void *packed, const int32_t *radii,
+                                           const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
+                                           unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
+                                           float exposure_time, const void *ws_g, void *ws_e, size_t ws_e_bytes,
+                                           int32_t *gaussian_ids_sorted, int32_t *tile_bins, int32_t *status, void *stream) {
+    B200_REQUIRE(num_points >= 1 && capacity >= 1, "bad sizes");
+    B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
+    B200_REQUIRE(tile_bins && ws_g && status, "null pointer");
+    B200_REQUIRE(packed && radii && num_tiles_hit && gaussian_ids_sorted && ws_e, "null pointer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ws_e) & 255u) == 0, "workspace must be 256-byte aligned");
+    const CullGeom c = make_cull_geom(img_height, img_width, block_width, n_blur_samples, rolling_shutter_time, exposure_time);
+    const int num_tiles = c.tbx * c.tby;
+    cudaStream_t st = as_stream(stream);
+    B200_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, st));
+    const int n = num_points, m = capacity;
+    const CullWsG G = cull_ws_g(n);
+    const CullWsE E = cull_ws_e(m);
+    B200_REQUIRE(ws_e_bytes >= E.total, "workspace too small: %zu < %zu", ws_e_bytes, E.total);
+    const char *gb = static_cast<const char *>(ws_g);
+    const int32_t *counters = (const int32_t *)(gb + G.counters);
+    const int4 *bbox = (const int4 *)(gb + G.bbox);
+    const int32_t *chunk_off = (const int32_t *)(gb + G.chunk_off), *base_of = (const int32_t *)(gb + G.base_of);
+    const int32_t *chunks = (const int32_t *)(gb + G.chunks);
+    int32_t *cursor = (int32_t *)(const_cast<char *>(gb) + G.cursor);
+    uint32_t *masks = (uint32_t *)(const_cast<char *>(gb) + G.masks);
+    char *eb = static_cast<char *>(ws_e);
+    uint32_t *tkeys_a = (uint32_t *)(eb + E.tkeys_a), *tkeys_b = (uint32_t *)(eb + E.tkeys_b);
+    int32_t *ids_a = (int32_t *)(eb + E.ids_a);
+    void *cub_ws = eb + E.cub;
+    size_t cub_bytes = E.cub_bytes;
+    (c.per_sample ? cull_chunks_kernel<true, true> : cull_chunks_kernel<true, false>)<<<CULL_GRID, 256, 0, st>>>(
+        n, m, reinterpret_cast<const PackedGaussian *>(packed), bbox, chunk_off, chunks, c, counters, masks, G.mask_cap, nullptr,
+        base_of, cursor, tkeys_a, ids_a, (uint32_t)num_tiles, status);
+    B200_LAUNCH_CHECK();
+    int bits = key_end_bit(num_tiles + 1) - 32;  // the padding key num_tiles must sort too
+    if (bits < 1) bits = 1;
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, tkeys_a, tkeys_b, ids_a, gaussian_ids_sorted, m, 0, bits, st));
+    count_launch(1 + (bits + 7) / 8);
+    tile_bin_edges32_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, tkeys_b, reinterpret_cast<int2 *>(tile_bins), num_tiles);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

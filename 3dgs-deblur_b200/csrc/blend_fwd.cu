@@ -25,7 +25,22 @@ struct BlendFwdParams {
     float *final_Ts;          // (H,W,S)
     float *out_alpha;         // (H,W) or null: 1 - mean_s final_T, what rasterize.py:161-163 derives with two torch ops
     int32_t *final_idx;       // (H,W,S)
+    const int32_t *ref_isect;  // DEVICE int32 or null: the reference's num_intersects of this image, when the host never
+                               // learned it (capacity-mode binning); < 1 selects the reference's empty-render branch
 };
+
+// What the reference returns when nothing intersects a tile (rasterize.py:136-144): the background colour and all-zero
+// final_Ts / final_idx, hence alpha = 1.  Only reachable in the capacity mode, where the count lives on the device.
+template <int S>
+__device__ __forceinline__ void write_empty_render(const BlendFwdParams &p, bool inside, int i, int j) {
+    if (!inside) return;
+    const size_t pix = (size_t)i * p.g.W + j;
+#pragma unroll
+    for (int s = 0; s < S; ++s) { p.final_Ts[pix * S + s] = 0.f; p.final_idx[pix * S + s] = 0; }
+    p.out_img[3 * pix] = __ldg(p.background); p.out_img[3 * pix + 1] = __ldg(p.background + 1);
+    p.out_img[3 * pix + 2] = __ldg(p.background + 2);
+    if (p.out_alpha) p.out_alpha[pix] = 1.0f;
+}
 
 template <int S, int PPL>
 __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 6 : 1) blend_forward_kernel(const BlendFwdParams p) {
@@ -48,6 +63,11 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 6 : 1) blend_f
         inside[q] = has_pixel && pi[q] < p.g.H && pj[q] < p.g.W;
         px[q] = (float)pj[q] + 0.5f; py[q] = (float)pi[q] + 0.5f;
         roll[q] = (float)((double)p.g.rs_time * ((double)(py[q] / (float)p.g.H) - 0.5));  // forward.cu:360
+    }
+    if (p.ref_isect && __ldg(p.ref_isect) < 1) {  // block-uniform
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) write_empty_render<S>(p, inside[q], pi[q], pj[q]);
+        return;
     }
     float blur[S];  // blur_rel of forward.cu:363 without the roll part; tau = blur[s] + roll[q]
 #pragma unroll
@@ -224,6 +244,11 @@ __global__ void __launch_bounds__(128, 6) blend_forward_kernel2(const BlendFwdPa
         inside[q] = has_pixel && pi[q] < p.g.H && pj[q] < p.g.W;
         px[q] = (float)pj[q] + 0.5f; py[q] = (float)pi[q] + 0.5f;
         roll[q] = (float)((double)p.g.rs_time * ((double)(py[q] / (float)p.g.H) - 0.5));  // forward.cu:360
+    }
+    if (p.ref_isect && __ldg(p.ref_isect) < 1) {  // block-uniform
+#pragma unroll
+        for (int q = 0; q < 2; ++q) write_empty_render<S>(p, inside[q], pi[q], pj[q]);
+        return;
     }
     float blur[S];
 #pragma unroll
@@ -409,7 +434,8 @@ extern "C" size_t b200_packed_record_bytes(void) { return sizeof(PackedGaussian)
 static int run_blend_forward(unsigned img_height, unsigned img_width, unsigned block_width, unsigned n_blur_samples,
                              const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const void *packed,
                              float rolling_shutter_time, float exposure_time, const float *background, float *out_img,
-                             float *final_Ts, int32_t *final_idx, float *out_alpha, cudaStream_t st) {
+                             float *final_Ts, int32_t *final_idx, float *out_alpha, cudaStream_t st,
+                             const int32_t *ref_isect = nullptr) {
     B200_REQUIRE(n_blur_samples > 0 && n_blur_samples <= B200_MAX_BLUR_SAMPLES, "unsupported blur size");  // bindings.cu:450-452
     B200_REQUIRE(block_width > 1 && block_width <= 16, "block_width must be between 2 and 16");
     B200_REQUIRE(img_height > 0 && img_width > 0, "image size must be positive");
@@ -425,6 +451,7 @@ static int run_blend_forward(unsigned img_height, unsigned img_width, unsigned b
     p.packed = reinterpret_cast<const PackedGaussian *>(packed);
     p.background = background;
     p.out_img = out_img; p.final_Ts = final_Ts; p.final_idx = final_idx; p.out_alpha = out_alpha;
+    p.ref_isect = ref_isect;
     switch (n_blur_samples) {
         case 1: return launch_fwd<1>(p, st);
         case 2: return launch_fwd<2>(p, st);
@@ -474,4 +501,41 @@ extern "C" int b200_rasterize_forward(int num_points, unsigned img_height, unsig
     if (rc) return rc;
     return run_blend_forward(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed_ws,
                              rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx, nullptr, st);
+}
+
+
+// Capacity-mode companion of b200_blend_forward_packed: `status` is the DEVICE int32[4] block written by
+// b200_bin_cull_emit_capacity; status[3] (the reference's num_intersects) < 1 reproduces the reference's empty-render
+// branch (rasterize.py:136-144) without the host ever reading the count.
+extern "C" int b200_blend_forward_packed_status(unsigned img_height, unsigned img_width, unsigned block_width,
+                                                unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                                const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
+                                                float exposure_time, const float *background, const int32_t *status,
+                                                float *out_img, float *final_Ts, int32_t *final_idx, float *out_alpha,
+                                                void *stream) {
+    B200_REQUIRE(status, "null status pointer");
+    return run_blend_forward(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed,
+                             rolling_shutter_time, exposure_time, background, out_img, final_Ts, final_idx, out_alpha,
+                             as_stream(stream), status + 3);
+}
+
+namespace b200 {
+// colours are the one part of the packed record the tile binning does not read: a caller that bins before it has shaded
+// (the geometry of step k+1 is projected and binned while the SH exchange of step k is still in flight) packs with any
+// colours and patches them in afterwards.  12 of every 64 bytes; the cull data (thr, hx, hy) stays.
+static __global__ void __launch_bounds__(256) set_record_colors_kernel(int n, const float *__restrict__ colors,
+                                                                       PackedGaussian *__restrict__ rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rec[i].r = colors[3 * (size_t)i]; rec[i].g = colors[3 * (size_t)i + 1]; rec[i].b = colors[3 * (size_t)i + 2];
+}
+}  // namespace b200
+
+extern "C" int b200_set_record_colors(int num_points, const float *colors, void *packed, void *stream) {
+    B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
+    B200_REQUIRE(colors && packed && aligned16(packed), "null / misaligned pointer");
+    b200::set_record_colors_kernel<<<ceil_div(num_points, 256), 256, 0, as_stream(stream)>>>(
+        num_points, colors, reinterpret_cast<PackedGaussian *>(packed));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
 }

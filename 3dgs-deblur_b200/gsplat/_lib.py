@@ -51,6 +51,12 @@ SIGNATURES = {
     "b200_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_adam_step": (_i, [C.c_longlong, _p, _p, _p, _p, _i, _d, _d, _d, _d, _d, _i, _p]),
+    "b200_adam_state_bytes": (_sz, []),
+    "b200_adam_prepare": (_i, [_p, _p, _d, _d, _d, _p]),
+    "b200_adam_step_state": (_i, [C.c_longlong, _p, _p, _p, _p, _p, _d, _d, _d, _d, _i, _p]),
+    "b200_bin_cull_emit_capacity": (_i, [_i, _i, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _p, _sz, _p, _p, _p, _p]),
+    "b200_blend_forward_packed_status": (_i, [_u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "b200_set_record_colors": (_i, [_i, _p, _p, _p]),
     "b200_ssim_ws_bytes": (_sz, [_u, _u, _u]),
     "b200_ssim_maps_bytes": (_sz, [_u, _u, _u]),
     "b200_ssim_forward": (_i, [_u, _u, _u, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _p]),

@@ -136,8 +136,8 @@ def compute_sh_forward(method, num_points, degree, degrees_to_use, viewdirs, coe
     return colors
 
 
-def compute_sh_backward(method, num_points, degree, degrees_to_use, viewdirs, v_colors):
-    """-> v_coeffs (N,K,3)  [bindings.cu:105-151]"""
+def compute_sh_backward(method, num_points, degree, degrees_to_use, viewdirs, v_colors, *, out=None):
+    """-> v_coeffs (N,K,3)  [bindings.cu:105-151]; `out` (extension): write into this buffer instead of a new tensor"""
     if method not in _METHOD:
         raise RuntimeError(f"Invalid method: {method}")
     n = int(num_points)
@@ -148,7 +148,13 @@ def compute_sh_backward(method, num_points, degree, degrees_to_use, viewdirs, v_
     viewdirs, v_colors = viewdirs.contiguous(), v_colors.contiguous()
     require_cuda(viewdirs, v_colors)
     with on_device(v_colors.device):
-        v_coeffs = torch.empty((n, num_sh_bases(degree), 3), dtype=torch.float32, device=v_colors.device)
+        if out is not None:
+            require_cuda(out)
+            if out.dtype != torch.float32 or out.numel() != n * num_sh_bases(degree) * 3:
+                raise RuntimeError("compute_sh_backward: `out` must be float32 with N * K * 3 elements")
+            v_coeffs = out.view(n, num_sh_bases(degree), 3)
+        else:
+            v_coeffs = torch.empty((n, num_sh_bases(degree), 3), dtype=torch.float32, device=v_colors.device)
         check(_lib.load().b200_compute_sh_backward(_METHOD[method], n, int(degree), int(degrees_to_use),
                                                    ptr(_f32(viewdirs)), ptr(_f32(v_colors)), ptr(v_coeffs), stream()))
     return v_coeffs
@@ -275,8 +281,44 @@ def bin_cull(packed, depths, radii, num_tiles_hit, img_height, img_width, block_
     return total_ref, ids, bins
 
 
+def bin_cull_capacity(packed, depths, radii, num_tiles_hit, img_height, img_width, block_width, n_blur_samples,
+                      rolling_shutter_time, exposure_time, capacity, status):
+    """Extension: culled two-level binning WITHOUT a host sync -> (gaussian_ids_sorted (capacity,), tile_bins (tiles,2)).
+    The id list is sized by the caller (`capacity`, from a running high-water mark); `status` (device int32[4]) receives
+    [0] |= overflow, [1] entries, [2] max entries seen, [3] the reference's num_intersects (include/b200splat.h)."""
+    require_cuda(packed, depths, radii, num_tiles_hit, status)
+    dev = depths.device
+    with on_device(dev):
+        lib = _lib.load()
+        n = depths.numel()
+        H, W, bw, S = int(img_height), int(img_width), int(block_width), int(n_blur_samples)
+        rs, ex = float(rolling_shutter_time), float(exposure_time)
+        cap = int(capacity)
+        ws_bytes = lib.b200_bin_cull_ws_bytes(n)
+        ws_g = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        flag = _lib.take_pending_flag(dev)  # the deferred quaternion check stays on the device (polled by the trainer)
+        tiles = ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
+        bins = torch.empty((tiles, 2), dtype=torch.int32, device=dev)
+        ids = torch.empty((cap,), dtype=torch.int32, device=dev)
+        check(lib.b200_bin_cull_count(n, ptr(packed), ptr(_f32(depths)), ptr(radii), ptr(num_tiles_hit), H, W, bw, S, rs, ex,
+                                      ptr(ws_g), ws_bytes, None, ptr(flag), stream()))
+        e_bytes = lib.b200_bin_cull_emit_ws_bytes(cap)
+        ws_e = torch.empty((e_bytes,), dtype=torch.uint8, device=dev)
+        check(lib.b200_bin_cull_emit_capacity(n, cap, ptr(packed), ptr(radii), ptr(num_tiles_hit), H, W, bw, S, rs, ex, ptr(ws_g),
+                                              ptr(ws_e), e_bytes, ptr(ids), ptr(bins), ptr(status), stream()))
+    return ids, bins
+
+
+def set_record_colors(packed, colors):
+    """Extension: patch the colours of packed blend records in place (the binning does not read them)."""
+    require_cuda(packed, colors)
+    with on_device(packed.device):
+        check(_lib.load().b200_set_record_colors(colors.size(0), ptr(_f32(colors)), ptr(packed), stream()))
+    return packed
+
+
 def blend_forward_packed(img_height, img_width, block_width, n_blur_samples, gaussian_ids_sorted, tile_bins, packed,
-                         rolling_shutter_time, exposure_time, background, want_alpha=False):
+                         rolling_shutter_time, exposure_time, background, want_alpha=False, *, status=None):
     """Extension: blend forward on prepacked records -> (out_img, final_Ts, final_idx[, alpha]); alpha = 1 - mean_s
     final_Ts written by the same kernel (rasterize.py:161-163 computes it with two torch passes)."""
     require_cuda(gaussian_ids_sorted, tile_bins, packed, background)
@@ -287,10 +329,16 @@ def blend_forward_packed(img_height, img_width, block_width, n_blur_samples, gau
         final_Ts = torch.empty((H, W, S), dtype=torch.float32, device=dev)
         final_idx = torch.empty((H, W, S), dtype=torch.int32, device=dev)
         alpha = torch.empty((H, W), dtype=torch.float32, device=dev) if want_alpha else None
-        check(_lib.load().b200_blend_forward_packed(H, W, int(block_width), S, ptr(gaussian_ids_sorted), ptr(tile_bins),
-                                                    ptr(packed), float(rolling_shutter_time), float(exposure_time),
-                                                    ptr(_f32(background)), ptr(out_img), ptr(final_Ts), ptr(final_idx),
-                                                    ptr(alpha), stream()))
+        if status is not None:  # capacity-mode lists: the reference's empty-render branch is taken on the device
+            check(_lib.load().b200_blend_forward_packed_status(
+                H, W, int(block_width), S, ptr(gaussian_ids_sorted), ptr(tile_bins), ptr(packed), float(rolling_shutter_time),
+                float(exposure_time), ptr(_f32(background)), ptr(status), ptr(out_img), ptr(final_Ts), ptr(final_idx), ptr(alpha),
+                stream()))
+        else:
+            check(_lib.load().b200_blend_forward_packed(H, W, int(block_width), S, ptr(gaussian_ids_sorted), ptr(tile_bins),
+                                                        ptr(packed), float(rolling_shutter_time), float(exposure_time),
+                                                        ptr(_f32(background)), ptr(out_img), ptr(final_Ts), ptr(final_idx),
+                                                        ptr(alpha), stream()))
     if want_alpha:
         return out_img, final_Ts, final_idx, alpha
     return out_img, final_Ts, final_idx

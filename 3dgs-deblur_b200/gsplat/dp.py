@@ -30,15 +30,24 @@ FIELDS = ("means", "log_scales", "quats", "opacity_logit", "sh_dc", "sh_rest")
 class FlatGaussians:
     """Gaussian parameters as views into one flat buffer (+ a flat gradient buffer of the same layout)."""
 
-    def __init__(self, scene: Dict, device, n_cameras: int = 0, optimize_velocities: bool = False):
+    def __init__(self, scene: Dict, device, n_cameras: int = 0, optimize_velocities: bool = False, sh_layout: str = "split"):
+        """sh_layout "split": sh_dc (N,1,3) and sh_rest (N,K-1,3) are two parameters like Splatfacto's features_dc /
+        features_rest (the render block concatenates them every step, splatfacto.py:840-842; gsplat.fused reads them
+        separately).  "block": ONE (N,K,3) parameter `sh` in the layout spherical_harmonics consumes -- no per-step
+        torch.cat (a 57 MB copy at 300k Gaussians) and no cat backward; `sh_dc` / `sh_rest` remain readable as views."""
+        if sh_layout not in ("split", "block"):
+            raise ValueError("sh_layout must be 'split' or 'block'")
         N = scene["means"].shape[0]
         K = scene["sh_rest"].shape[1] + 1
-        self.N, self.K = N, K
+        self.N, self.K, self.sh_layout = N, K, sh_layout
         widths = dict(means=3, log_scales=3, quats=4, opacity_logit=1, sh_dc=3, sh_rest=3 * (K - 1))
         shapes = dict(means=(N, 3), log_scales=(N, 3), quats=(N, 4), opacity_logit=(N, 1), sh_dc=(N, 1, 3),
                       sh_rest=(N, K - 1, 3))
         extra = 6 * n_cameras if optimize_velocities else 0
-        total = N * sum(widths.values()) + extra
+        # "block": pad the camera rows so the SH block starts on a 16-byte boundary (the slice-wise device-state Adam and
+        # the SH kernels' vector accesses want that)
+        pad = (-(N * 11 + extra)) % 4 if sh_layout == "block" else 0
+        total = N * sum(widths.values()) + extra + pad
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.flat_grad = torch.zeros_like(self.flat)
         self.params: Dict[str, torch.Tensor] = {}
@@ -54,15 +63,32 @@ class FlatGaussians:
 
         off = 0
         for name in FIELDS:
-            if name == "sh_dc" and extra:  # camera rows sit between the geometry block and the SH block
-                self.cam_vel = take("cam_vel", off, extra, (n_cameras, 6))
-                off += extra
+            if name == "sh_dc":  # camera rows (+ alignment padding) sit between the geometry block and the SH block
+                if extra:
+                    self.cam_vel = take("cam_vel", off, extra, (n_cameras, 6))
+                off += extra + pad
+                if sh_layout == "block":
+                    blk = self.flat[off:off + N * 3 * K].view(N, K, 3)
+                    blk[:, :1].copy_(scene["sh_dc"].to(device).reshape(N, 1, 3))
+                    blk[:, 1:].copy_(scene["sh_rest"].to(device).reshape(N, K - 1, 3))
+                    self.params["sh"] = take("sh", off, N * 3 * K, (N, K, 3))
+                    self.slices["sh_dc"] = self.slices["sh_rest"] = self.slices["sh"]
+                    off += N * 3 * K
+                    break
             self.flat[off:off + N * widths[name]].view(shapes[name]).copy_(scene[name].to(device).reshape(shapes[name]))
             self.params[name] = take(name, off, N * widths[name], shapes[name])
             off += N * widths[name]
         assert off == total
         self.sh_start = self.slices["sh_dc"][0]  # flat[sh_start:] = all SH coefficients
         self.floats_per_gaussian = sum(widths.values())
+        if sh_layout == "block":  # read-only conveniences for code written against Splatfacto's two tensors
+            self.views = {"sh_dc": self.params["sh"][:, :1], "sh_rest": self.params["sh"][:, 1:]}
+
+    def sh_coeffs(self) -> torch.Tensor:
+        """(N, K, 3) coefficients as spherical_harmonics wants them."""
+        if self.sh_layout == "block":
+            return self.params["sh"]
+        return torch.cat((self.params["sh_dc"], self.params["sh_rest"]), dim=1)  # splatfacto.py:840-842
 
     def parameters(self) -> List[torch.Tensor]:
         ps = list(self.params.values())
@@ -89,7 +115,7 @@ def render(model: FlatGaussians, cam: Dict, scene: Dict, cam_index: int = 0, sh_
     xys, depths, pix_vels, radii, conics, comp, num_tiles_hit, _ = project_gaussians(
         p["means"], torch.exp(p["log_scales"]), 1, quats, lin, ang, scene["rolling_shutter_time"],
         scene["exposure_time"], cam["viewmat"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, bw)
-    colors = torch.cat((p["sh_dc"], p["sh_rest"]), dim=1)
+    colors = model.sh_coeffs()
     viewdirs = p["means"].detach() - cam["cam_pos"]
     rgbs = torch.clamp(spherical_harmonics(sh_degree_to_use, viewdirs, colors) + 0.5, min=0.0)
     opacities = torch.sigmoid(p["opacity_logit"]) * comp[:, None]  # "antialiased" mode, splatfacto.py:853-854
@@ -182,7 +208,8 @@ class ImageShardedTrainer:
         # exchange / update pipeline still applies
         self.overlap_sh = bool(overlap_sh and self.distributed and not self.fused)
         if self.overlap_sh:
-            for name in ("sh_dc", "sh_rest"):
+            self._sh_params = ("sh",) if model.sh_layout == "block" else ("sh_dc", "sh_rest")
+            for name in self._sh_params:
                 model.params[name].register_post_accumulate_grad_hook(self._on_sh_grad)
 
     def _reduce_async(self, chunk_ids):
@@ -190,7 +217,7 @@ class ImageShardedTrainer:
 
     def _on_sh_grad(self, _param):
         self._sh_seen += 1
-        if self._sh_seen == 2:  # both halves of the cat() have landed in the flat buffer
+        if self._sh_seen == len(self._sh_params):  # every SH parameter's gradient has landed in the flat buffer
             self._sh_works = self._reduce_async(range(1, len(self._chunks)))
 
     def image_index(self, step: int, n_images: int) -> int:
@@ -247,3 +274,360 @@ class ImageShardedTrainer:
             dist.all_reduce(vis_counts, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(max_2d, op=dist.ReduceOp.MAX, group=self.group)
         return grad_norm_sum, vis_counts, max_2d
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pipelined trainer: no host sync on the path, two CUDA graphs per camera signature, the gradient exchange and the SH
+# update of step k hidden behind the geometry of image k+1.
+# ------------------------------------------------------------------------------------------------------------------
+
+def geometry_phase(model: FlatGaussians, st: Dict, scene: Dict, capacity: int, status: torch.Tensor):
+    """Phase A of a step -- everything that depends only on the GEOMETRY parameters (means, scales, quaternions,
+    opacities, camera rows): the projection block of splatfacto.py:816-834 on the public operator, the opacity
+    activation (:853-856) and the tile lists (gsplat.rasterize.prepare_lists: capacity mode, no host sync).
+    `st` holds the step's camera as device tensors: cam (21 floats: viewmat 12 | lin_vel 3 | ang_vel 3 | cam_pos 3)
+    and cam_index (int64[1])."""
+    from gsplat import project_gaussians
+    from gsplat.rasterize import prepare_lists
+
+    p = model.params
+    cam = st["cam"]
+    viewmat, vel0, cam_pos = cam[:12].view(3, 4), cam[12:18], cam[18:21]
+    if model.cam_vel is not None:  # per-camera velocity rows (disjoint across images): row cam_index + dataset value
+        vel = model.cam_vel.index_select(0, st["cam_index"])[0] + vel0
+    else:
+        vel = vel0
+    lin, ang = vel[:3].unsqueeze(0), vel[3:].unsqueeze(0)
+    H, W, bw = scene["H"], scene["W"], scene["block_width"]
+    rs, ex = scene["rolling_shutter_time"], scene["exposure_time"]
+    quats = p["quats"] / p["quats"].norm(dim=-1, keepdim=True)
+    xys, depths, pix_vels, radii, conics, comp, num_tiles_hit, _ = project_gaussians(
+        p["means"], torch.exp(p["log_scales"]), 1, quats, lin, ang, rs, ex, viewmat, scene["fx"], scene["fy"], scene["cx"],
+        scene["cy"], H, W, bw)
+    opacities = torch.sigmoid(p["opacity_logit"]) * comp[:, None]  # "antialiased" mode, splatfacto.py:853-854
+    blur = scene["blur_samples"] if ex > 0 else 1
+    prep = prepare_lists(xys, depths, pix_vels, radii, conics, num_tiles_hit, opacities, H, W, bw, rs, ex, blur,
+                         capacity=capacity, status=status)
+    return dict(xys=xys, depths=depths, pix_vels=pix_vels, radii=radii, conics=conics, num_tiles_hit=num_tiles_hit,
+                opacities=opacities, prep=prep, cam_pos=cam_pos, blur=blur)
+
+
+def shading_phase(model: FlatGaussians, geo: Dict, scene: Dict, target: torch.Tensor, loss_fn, sh_degree_to_use: int = 3):
+    """Phase B -- needs the SH parameters: colours (splatfacto.py:840-852), blend on the prepared lists, loss, and the
+    backward pass through BOTH phases.  With the block layout the SH gradient goes straight into the flat gradient
+    buffer (gsplat.sh.coeff_grad_sink).  Returns the (device) loss."""
+    from gsplat import rasterize_gaussians, spherical_harmonics
+    from gsplat.sh import coeff_grad_sink
+
+    p = model.params
+    H, W, bw = scene["H"], scene["W"], scene["block_width"]
+    viewdirs = p["means"].detach() - geo["cam_pos"]
+    sink = model.flat_grad[model.sh_start:model.sh_start + model.N * model.K * 3] if model.sh_layout == "block" else None
+    with coeff_grad_sink(sink):
+        rgbs = torch.clamp(spherical_harmonics(sh_degree_to_use, viewdirs, model.sh_coeffs()) + 0.5, min=0.0)
+    rgb, alpha = rasterize_gaussians(geo["xys"], geo["depths"], geo["pix_vels"], geo["radii"], geo["conics"],
+                                     geo["num_tiles_hit"], rgbs, geo["opacities"], H, W, bw,
+                                     rolling_shutter_time=scene["rolling_shutter_time"], exposure_time=scene["exposure_time"],
+                                     blur_samples=geo["blur"], background=scene["background"], return_alpha=True,
+                                     prepared=geo["prep"])
+    loss = loss_fn(rgb, target)
+    loss.backward()
+    return loss.detach()
+
+
+class PipelinedTrainer:
+    """Image-sharded trainer on the drop-in operators with nothing on the path waiting for the host.
+
+    A step is cut where the parameter dependencies cut it:
+      A(k)  geometry of image k: projection + opacity + tile lists   -- reads the geometry rows only
+      B(k)  SH colours, blend, loss, backward through A and B         -- reads the SH block too
+    and the host queues, per step k:  B(k) | exchange(geometry grads), exchange(SH grads) | Adam(geometry) | A(k+1) ||
+    Adam(SH) on a side stream.  The SH block is 48 of the 59 floats per Gaussian: its allreduce and its update run behind
+    the projection + binning of the NEXT image, which only needs the geometry rows -- exact, because the SH parameters
+    are first read by B(k+1) (which waits for the side stream).  On one GPU the same ordering overlaps the bandwidth-bound
+    SH update with the latency-bound binning.
+
+    No host sync: the tile lists are sized from a running high-water mark (gsplat.rasterize.prepare_lists); if an image
+    needs more, its lists are incomplete -- the device raises a flag, the (rank-reduced) flag VETOES that step's
+    optimizer update on the device (gsplat.optim.FlatAdam device state), and the host, which polls a pinned copy of the
+    status words one step late, grows the capacity and reports the step in `vetoed` so the caller repeats the image.
+    With `use_graphs` A and B are captured as CUDA graphs per camera signature (image size, intrinsics, blur settings,
+    SH degree, capacity): the ~60 launches of a step become two graph launches; per-step inputs (camera, target) live in
+    static device buffers.
+
+    API:  prepare(cam, cam_index)            -- A for the first image (and after anything that invalidates it)
+          train_step(target, next_cam=None, next_index=0) -> device loss
+    `cam` = dict(viewmat (3,4), lin_vel (3), ang_vel (3), cam_pos (3)) tensors on any device, or `cam_floats`
+    (21 floats in that order, e.g. a pinned host row from gsplat.data.ImagePrefetcher)."""
+
+    def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, loss_fn=None, use_graphs: bool = True,
+                 capacity: Optional[int] = None, sh_degree_to_use: int = 3, geometry_fn=None, shading_fn=None,
+                 optimizer: str = "b200"):
+        self.model, self.scene = model, dict(scene)
+        if loss_fn is None:
+            from gsplat.losses import l1_loss as loss_fn
+        self.loss_fn = loss_fn
+        self.sh_degree = sh_degree_to_use
+        self.geometry_fn = geometry_fn or geometry_phase   # (tests inject CPU stand-ins with the same interface)
+        self.shading_fn = shading_fn or shading_phase
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = group
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        dev = model.flat.device
+        self.device = dev
+        self.cuda = dev.type == "cuda"
+        self.use_graphs = bool(use_graphs and self.cuda)
+        self._avg = self.distributed and dist.get_backend(group) == "nccl"
+        self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        # static per-step inputs / outputs
+        self.st = dict(cam=torch.zeros(21, dtype=torch.float32, device=dev), cam_index=torch.zeros(1, dtype=torch.int64, device=dev))
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)       # [overflow, entries, max entries, reference isects]
+        self.flag = self.status[0:1]                                      # this step's veto (reduced with MAX across ranks)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.capacity = capacity
+        self.vetoed: List[int] = []     # step indices whose update was skipped (the caller repeats those images)
+        self.steps = 0
+        self._geo = None
+        self._graphs: Dict[tuple, Dict] = {}
+        self._flag_work = None
+        self._pending_sh = None
+        self.optimizer = optimizer
+        if optimizer == "b200":
+            from gsplat.optim import FlatAdam
+            self.adam = FlatAdam(model.flat, model.flat_grad, lr=lr, eps=1e-15).use_device_state()
+        elif optimizer == "torch":  # CPU / gloo tests of this host logic: same slices, torch's Adam, host-side veto
+            self.adam = None
+            lo, total = model.sh_start, model.flat.numel()
+            self._torch_opts = []
+            for a, b_ in ((0, lo), (lo, total)):
+                alias = model.flat[a:b_].detach().requires_grad_(True)
+                alias.grad = model.flat_grad[a:b_]
+                self._torch_opts.append(torch.optim.Adam([alias], lr=lr, eps=1e-15))
+        else:
+            raise ValueError("optimizer must be 'b200' or 'torch'")
+        if self.cuda:
+            self.side = torch.cuda.Stream(device=dev)
+            self.ev_prepared, self.ev_sh_done = torch.cuda.Event(), torch.cuda.Event()
+            self._host_words = torch.zeros(2, 24, dtype=torch.int32).pin_memory()   # status (4) | adam state (16) | quat flag
+            self._host_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._host_seen = [False, False]
+            self._vetoed_seen = 0
+
+    # ---- camera / capacity --------------------------------------------------------------------------------------
+    def _set_camera(self, cam, cam_index):
+        if torch.is_tensor(cam):  # 21 floats: viewmat 12 | lin_vel 3 | ang_vel 3 | cam_pos 3 (host pinned or device)
+            row = cam.reshape(-1)[:21]
+        else:
+            d0 = cam["viewmat"].device
+            row = torch.cat([cam["viewmat"].reshape(-1)[:12], cam["lin_vel"].reshape(-1)[:3].to(d0),
+                             cam["ang_vel"].reshape(-1)[:3].to(d0), cam["cam_pos"].reshape(-1)[:3].to(d0)]).float()
+            for k in ("fx", "fy", "cx", "cy"):  # intrinsics are launch constants (part of the graph key)
+                if k in cam:
+                    self.scene[k] = float(cam[k])
+        self.st["cam"].copy_(row, non_blocking=True)
+        self.st["cam_index"].fill_(int(cam_index))
+
+    def _size_capacity(self):
+        """First use: one synchronous probe of the entry count with a generous capacity; later growth comes from the
+        polled high-water mark."""
+        if self.capacity is not None:
+            return
+        if not self.cuda:
+            self.capacity = 1
+            return
+        probe = max(1 << 20, 8 * self.model.N)
+        with torch.no_grad():
+            self.geometry_fn(self.model, self.st, self.scene, probe, self.status)
+        torch.cuda.current_stream().synchronize()
+        entries = int(self.status[1])
+        if int(self.status[0]):
+            entries = max(entries, probe)
+        self.status.zero_()
+        self.capacity = self._round_capacity(int(1.6 * entries) + 65536)
+
+    @staticmethod
+    def _round_capacity(n):
+        return (int(n) + 65535) // 65536 * 65536
+
+    # ---- phases (eager or captured) ------------------------------------------------------------------------------
+    def _key(self):
+        s = self.scene
+        return (s["H"], s["W"], s["fx"], s["fy"], s["cx"], s["cy"], s["block_width"], s["blur_samples"], s["exposure_time"],
+                s["rolling_shutter_time"], self.sh_degree, self.capacity, self.model.N)
+
+    def _entry(self, target_shape_dtype):
+        key = self._key() + (target_shape_dtype,)
+        e = self._graphs.get(key)
+        if e is None:
+            e = self._graphs[key] = dict(gA=None, gB=None, geo=None, target=None, warm=0)
+        return e
+
+    def _run_A(self, e):
+        if self.use_graphs and e["gA"] is not None:
+            e["gA"].replay()
+            self._geo = e["geo"]
+            return
+        if self.use_graphs and e["warm"] >= 2:  # two eager warm-up rounds (allocator, lazy inits), then capture
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                e["geo"] = self.geometry_fn(self.model, self.st, self.scene, self.capacity, self.status)
+            e["gA"] = g
+            g.replay()  # (capture does not execute)
+            self._geo = e["geo"]
+            return
+        self._geo = self.geometry_fn(self.model, self.st, self.scene, self.capacity, self.status)
+        e["geo_eager"] = True
+
+    def _run_B(self, e, target):
+        if self.use_graphs and e["gB"] is not None:
+            e["target"].copy_(target, non_blocking=True)
+            e["gB"].replay()
+            return
+        if self.use_graphs and e["gA"] is not None and e["warm"] >= 2:
+            # B is captured against the tensors A's graph writes (static addresses), with a static target buffer
+            e["target"] = torch.empty_like(target)
+            e["target"].copy_(target)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                tgt = e["target"].float() / 255 if e["target"].dtype == torch.uint8 else e["target"]
+                self.loss.copy_(self.shading_fn(self.model, e["geo"], self.scene, tgt, self.loss_fn, self.sh_degree))
+            e["gB"] = g
+            g.replay()
+            return
+        tgt = target.float() / 255 if target.dtype == torch.uint8 else target
+        self.loss.copy_(self.shading_fn(self.model, self._geo, self.scene, tgt, self.loss_fn, self.sh_degree))
+        e["warm"] += 1
+
+    # ---- public API ----------------------------------------------------------------------------------------------
+    def prepare(self, cam, cam_index: int = 0):
+        """Stage the camera of the image the next train_step trains on (phase A itself is queued by train_step: at once
+        for the first image, behind the previous step's geometry update afterwards)."""
+        self._set_camera(cam, cam_index)
+        self._size_capacity()
+        self._prepared = True
+        self._A_done = False
+
+    def _ensure_A(self, e):
+        if not self._A_done:
+            self._run_A(e)
+            self._A_done = True
+            if self.distributed:  # this image's overflow flag, agreed on by all ranks before anyone's Adam reads it
+                self._flag_work = dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group, async_op=True)
+
+    def train_step(self, target: torch.Tensor, next_cam=None, next_index: int = 0):
+        """Trains on the prepared image (B, exchange, update) and, given `next_cam`, runs A for the next image while the
+        SH block is still being exchanged / updated.  Returns the device loss (a static tensor: copy it if you keep it)."""
+        assert getattr(self, "_prepared", False), "call prepare(cam, cam_index) before the first train_step"
+        m = self.model
+        e = self._entry((tuple(target.shape), target.dtype))
+        self._ensure_A(e)
+        if self.cuda and self._pending_sh is not None:
+            torch.cuda.current_stream().wait_event(self.ev_sh_done)   # SH parameters of the previous step are final
+            self._pending_sh = None
+        self._run_B(e, target)
+        lo, total = m.sh_start, m.flat.numel()
+        works = None
+        if self.distributed:
+            works = [dist.all_reduce(m.flat_grad[:lo], op=self._op, group=self.group, async_op=True),
+                     dist.all_reduce(m.flat_grad[lo:], op=self._op, group=self.group, async_op=True)]
+            self._flag_work.wait()
+        scale = 1.0 if (self._avg or not self.distributed) else 1.0 / self.world
+        veto_host = False
+        if self.adam is not None:
+            self.adam.prepare(self.flag)
+            if self.cuda:
+                self.ev_prepared.record()
+        else:  # torch optimizer (CPU tests): the veto is read on the host
+            veto_host = bool(int(self.flag[0]) != 0)
+            self.flag.zero_()
+            if veto_host:
+                self.vetoed.append(self.steps)
+        if works is not None:
+            works[0].wait()
+        self._update(0, lo, scale, veto_host, 0)
+        self._poll_host()
+        # ---- next image's geometry (needs only the rows just updated), SH update beside it
+        self._prepared = False
+        if next_cam is not None:
+            self.prepare(next_cam, next_index)
+        if self.cuda:
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.ev_prepared)
+                if works is not None:
+                    works[1].wait()
+                self._update(lo, total, scale, veto_host, 1)
+                self.ev_sh_done.record(self.side)
+            self._pending_sh = True
+            if next_cam is not None:
+                self._ensure_A(self._entry((tuple(target.shape), target.dtype)))
+        else:
+            if works is not None:
+                works[1].wait()
+            self._update(lo, total, scale, veto_host, 1)
+        self.steps += 1
+        return self.loss
+
+    def _update(self, a, b_, scale, veto_host, which):
+        if self.adam is not None:
+            self.adam.update_state(a, b_, scale, True)
+            return
+        g = self.model.flat_grad[a:b_]
+        if not veto_host:
+            if scale != 1.0:
+                g.mul_(scale)
+            self._torch_opts[which].step()
+        g.zero_()
+
+    def finish(self):
+        """Drain the side stream (call before reading parameters)."""
+        if self.cuda and self._pending_sh is not None:
+            torch.cuda.current_stream().wait_event(self.ev_sh_done)
+            self._pending_sh = None
+
+    # ---- lagged host view of the device status (overflow / vetoes / input check) ---------------------------------
+    def _poll_host(self):
+        if not self.cuda or self.adam is None:
+            return
+        slot = self.steps & 1
+        other = 1 - slot
+        if self._host_seen[other] and self._host_ev[other].query():
+            self._consume(self._host_words[other])
+            self._host_seen[other] = False
+        w = self._host_words[slot]
+        w[0:4].copy_(self.status, non_blocking=True)
+        w[4:20].copy_(self.adam.state, non_blocking=True)
+        from gsplat import _lib
+        qf = _lib._quat_flags.get(self.device.index)
+        if qf is not None:
+            w[20:21].copy_(qf, non_blocking=True)
+        self._host_ev[slot].record()
+        self._host_seen[slot] = True
+
+    def _consume(self, w):
+        words = w.tolist()
+        if words[20]:
+            from gsplat import _lib
+            _lib.raise_if_flagged(words[20])  # deferred project_gaussians.py:69
+        vetoed = words[4 + 5]
+        if vetoed > self._vetoed_seen:
+            ring = words[4 + 6:4 + 16]
+            for j in range(self._vetoed_seen, vetoed):
+                if vetoed - j <= 10:
+                    self.vetoed.append(ring[j % 10])
+            self._vetoed_seen = vetoed
+            self.capacity = self._round_capacity(max(self.capacity, int(1.3 * words[2]) + 65536))  # new graphs at the new size
+        elif words[2] > 0.9 * self.capacity:  # growing scene: enlarge before it overflows
+            self.capacity = self._round_capacity(int(1.3 * words[2]) + 65536)
+
+    def sync_status(self):
+        """Blocking variant of the poll (end of training / tests): returns dict(entries_max, capacity, vetoed)."""
+        if self.cuda and self.adam is not None:
+            torch.cuda.synchronize(self.device)
+            for slot in (0, 1):
+                if self._host_seen[slot]:
+                    self._consume(self._host_words[slot])
+                    self._host_seen[slot] = False
+            w = torch.cat([self.status, self.adam.state]).tolist()
+            self._consume(w + [0] * 4)
+        return dict(entries_max=int(self.status[2]), capacity=self.capacity, vetoed=list(self.vetoed), steps=self.steps)

@@ -25,6 +25,33 @@ class FlatAdam:
         self._ptrs = (flat.data_ptr(), flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr())
         self._lib = _lib.load()
 
+    # ---- device-resident step state (no host sync, CUDA-graph friendly) ------------------------------------------
+    def use_device_state(self):
+        """Switch to the device-resident step count / bias corrections / veto (b200_adam_prepare,
+        b200_adam_step_state): `prepare(veto_flag)` once per step, then `update_state(begin, end)` per slice."""
+        if getattr(self, "state", None) is None:
+            nbytes = self._lib.b200_adam_state_bytes()
+            self.state = torch.zeros(nbytes // 4, dtype=torch.int32, device=self.flat.device)
+        return self
+
+    def prepare(self, veto_flag=None):
+        """Once per step, before the first `update_state`.  veto_flag: device int32[1] (or None); non-zero skips this step's
+        update on the device (gradients are still cleared) and is reset to zero."""
+        with _lib.on_device(self.flat.device):
+            check(self._lib.b200_adam_prepare(self.state.data_ptr(), None if veto_flag is None else veto_flag.data_ptr(),
+                                              self.lr, self.betas[0], self.betas[1], stream()))
+
+    def update_state(self, begin: int = 0, end: int = None, grad_scale: float = 1.0, zero_grad: bool = True):
+        end = self.flat.numel() if end is None else end
+        if not (0 <= begin <= end <= self.flat.numel()) or begin % 4:
+            raise ValueError(f"FlatAdam.update_state: bad slice [{begin}, {end}) (must start on a 16-byte boundary)")
+        off = 4 * begin
+        p, g, m, v = self._ptrs
+        with _lib.on_device(self.flat.device):
+            check(self._lib.b200_adam_step_state(end - begin, p + off, g + off, m + off, v + off, self.state.data_ptr(),
+                                                 self.betas[0], self.betas[1], self.eps, float(grad_scale),
+                                                 1 if zero_grad else 0, stream()))
+
     def begin_step(self):
         """Once per optimisation step, before the first `update` of that step."""
         self.step_count += 1

@@ -27,9 +27,43 @@ def _prepare(xys, colors, background, block_width):
     return colors, background
 
 
+class PreparedLists:
+    """Tile lists of one image built ahead of the shading (`prepare_lists`): the packed records (colours still to be
+    patched in), the culled id lists at a caller-chosen capacity, the tile ranges and the device status block."""
+
+    __slots__ = ("packed", "ids", "bins", "status", "cfg")
+
+    def __init__(self, packed, ids, bins, status, cfg):
+        self.packed, self.ids, self.bins, self.status, self.cfg = packed, ids, bins, status, cfg
+
+
+def prepare_lists(xys, depths, pix_vels, radii, conics, num_tiles_hit, opacity, img_height, img_width, block_width,
+                  rolling_shutter_time=0, exposure_time=0, blur_samples=1, *, capacity, status):
+    """Extension (not in the reference): pack + culled binning of one RGB image WITHOUT the host sync, before colours
+    exist.  Everything the binning reads -- centres, pixel velocities, conics, opacities -- is colour independent, so a
+    trainer can bin image k+1 while the colour parameters of step k are still being exchanged / updated, and nothing
+    waits for the list length: `capacity` slots are allocated (the caller tracks a high-water mark) and `status`, a device
+    int32[4] tensor the caller owns, receives [0] |= overflow, [1] entries, [2] running max, [3] the reference's
+    num_intersects.  Pass the result to `rasterize_gaussians(..., prepared=...)` with the same per-Gaussian tensors.
+    On overflow the lists are incomplete: the caller must discard that render (gsplat.optim.FlatAdam vetoes the step
+    on the device) and repeat the image with a larger capacity."""
+    assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
+    n_samples = int(blur_samples)
+    if not (0 < n_samples <= _MAX_BLUR_SAMPLES):
+        raise RuntimeError("unsupported blur size")
+    with torch.no_grad():
+        g = [t.detach().contiguous() for t in (xys, pix_vels, conics, opacity, depths, radii, num_tiles_hit)]
+        # colours: any (N, 3) float buffer -- patched by rasterize_gaussians before the blend reads them
+        packed = _C.pack_records(g[0], g[1], g[2], g[2], g[3])
+        ids, bins = _C.bin_cull_capacity(packed, g[4], g[5], g[6], img_height, img_width, block_width, n_samples,
+                                         rolling_shutter_time, exposure_time, capacity, status)
+    cfg = (int(img_height), int(img_width), int(block_width), n_samples, float(rolling_shutter_time), float(exposure_time))
+    return PreparedLists(packed, ids, bins, status, cfg)
+
+
 def rasterize_gaussians(xys, depths, pix_vels, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width,
                         block_width, background=None, return_alpha=False, rolling_shutter_time=0, exposure_time=0,
-                        blur_samples=1):
+                        blur_samples=1, prepared=None):
     """Blend the projected Gaussians into an (H, W, C) image; with `return_alpha` also the (H, W) coverage
     1 - mean_s(final transmittance).
 
@@ -41,8 +75,12 @@ def rasterize_gaussians(xys, depths, pix_vels, radii, conics, num_tiles_hit, col
     (the densification criterion the caller reads, rasterize.py:272-275)."""
     colors, background = _prepare(xys, colors, background, block_width)
     per_gaussian = [t.contiguous() for t in (xys, depths, pix_vels, radii, conics, num_tiles_hit, colors, opacity)]
+    if prepared is not None:
+        want = (int(img_height), int(img_width), int(block_width), int(blur_samples), float(rolling_shutter_time), float(exposure_time))
+        if prepared.cfg != want or colors.shape[-1] != 3:
+            raise ValueError(f"rasterize_gaussians: `prepared` was built for {prepared.cfg}, called with {want}")
     return _RasterizeGaussians.apply(*per_gaussian, img_height, img_width, block_width, background.contiguous(),
-                                     return_alpha, rolling_shutter_time, exposure_time, blur_samples)
+                                     return_alpha, rolling_shutter_time, exposure_time, blur_samples, prepared)
 
 
 def _empty_render(H, W, channels, n_samples, background, device):
@@ -57,10 +95,24 @@ def _empty_render(H, W, channels, n_samples, background, device):
 class _RasterizeGaussians(Function):
     @staticmethod
     def forward(ctx, xys, depths, pix_vels, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width,
-                block_width, background, return_alpha=False, rolling_shutter_time=0, exposure_time=0, blur_samples=1):
+                block_width, background, return_alpha=False, rolling_shutter_time=0, exposure_time=0, blur_samples=1,
+                prepared=None):
         H, W, bw = img_height, img_width, block_width
         rgb = colors.shape[-1] == 3
         packed = alpha = None
+        if prepared is not None:
+            # lists built ahead by prepare_lists (capacity mode, no host sync): patch this step's colours into the
+            # records and blend; the list length, an overflow and the empty-render case are all decided on the device
+            packed = _C.set_record_colors(prepared.packed, colors)
+            ids_sorted, tile_bins = prepared.ids, prepared.bins
+            img, final_Ts, final_idx, alpha = _C.blend_forward_packed(H, W, bw, blur_samples, ids_sorted, tile_bins, packed,
+                                                                      rolling_shutter_time, exposure_time, background,
+                                                                      want_alpha=True, status=prepared.status)
+            ctx.cfg = (H, W, bw, blur_samples, rolling_shutter_time, exposure_time, 1, True)
+            ctx.save_for_backward(ids_sorted, tile_bins, xys, pix_vels, conics, colors, opacity, background, final_Ts,
+                                  final_idx, packed)
+            ctx.set_materialize_grads(False)
+            return (img, alpha) if return_alpha else img
         if rgb:
             # RGB path: pack once, culled two-level binning (ONE host sync: the culled entry count), blend.  The id
             # lists hold only the (tile, Gaussian) pairs that can colour a pixel, in the reference's order; every
@@ -134,4 +186,4 @@ class _RasterizeGaussians(Function):
         # one slot per forward argument: xys, depths, pix_vels, radii, conics, num_tiles_hit, colors, opacity, then the 8
         # non-tensor / background arguments
         return (v_xy, None, v_pix_vels, None, v_conic, None, v_colors, v_opacity, None, None, None, v_background,
-                None, None, None, None)
+                None, None, None, None, None)

@@ -303,6 +303,45 @@ B200_API int b200_adam_step(long long numel, float *param, float *grad, float *e
                             double lr, double beta1, double beta2, double eps, double grad_scale, int zero_grad,
                             void *stream);
 
+/* Device-resident optimizer state: the step count, the bias corrections and a per-step VETO live on the device, so a
+ * trainer that never synchronises with the host (CUDA-graph replays, capacity-mode binning below) can still skip the
+ * update of a step whose render turned out incomplete.  state: DEVICE, b200_adam_state_bytes() bytes, zeroed by the caller
+ * before the first step; as int32 words: [2] optimizer steps applied, [3] current step vetoed (0/1), [4] steps prepared,
+ * [5] steps vetoed, [6..15] indices (0-based, in `steps prepared` numbering) of the last 10 vetoed steps, slot = count % 10.
+ *   b200_adam_prepare: once per step before the first update.  veto_flag: DEVICE int32 or null; non-zero = veto this step
+ *       (a data-parallel caller reduces it with MAX across ranks first); it is cleared here.
+ *   b200_adam_step_state: b200_adam_step with step / bias corrections / veto read from `state`; a vetoed step leaves
+ *       param and moments untouched and still clears the gradient slice.  The slice must start 16-byte aligned. */
+B200_API size_t b200_adam_state_bytes(void);
+B200_API int b200_adam_prepare(void *state, int32_t *veto_flag, double lr, double beta1, double beta2, void *stream);
+B200_API int b200_adam_step_state(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                                  const void *state, double beta1, double beta2, double eps, double grad_scale,
+                                  int zero_grad, void *stream);
+
+/* ---- rasterization without a host sync ---------------------------------------------------------------------------
+ * The reference reads the intersection count back to size its lists (gsplat/utils.py:123-124 `.item()`); the two-phase
+ * culled binning above reads the culled count.  In CAPACITY mode the caller sizes the lists from a running high-water
+ * mark instead: b200_bin_cull_count with totals_host_pinned = NULL, then b200_bin_cull_emit_capacity.  The id list has
+ * `capacity` slots: the real entries in the reference's order, then padding that belongs to no tile.
+ * status: DEVICE int32[4]: [0] |= 1 if this image's entries did not fit (lists incomplete: discard the render -- veto the
+ * optimizer step with b200_adam_prepare, grow the capacity, repeat the image), [1] entries of this image, [2] running
+ * maximum, [3] the reference's num_intersects of this image.  b200_blend_forward_packed_status = b200_blend_forward_packed
+ * plus the reference's empty-render branch (rasterize.py:136-144: background image, final_Ts = 0, alpha = 1) taken on
+ * the device when status[3] < 1.  b200_set_record_colors patches the colours of packed records (everything the binning
+ * reads is colour-independent, so a caller may bin before it has shaded). */
+B200_API int b200_bin_cull_emit_capacity(int num_points, int capacity, const void *packed, const int32_t *radii,
+                                         const int32_t *num_tiles_hit, unsigned img_height, unsigned img_width,
+                                         unsigned block_width, unsigned n_blur_samples, float rolling_shutter_time,
+                                         float exposure_time, const void *ws_g, void *ws_e, size_t ws_e_bytes,
+                                         int32_t *gaussian_ids_sorted, int32_t *tile_bins, int32_t *status, void *stream);
+B200_API int b200_blend_forward_packed_status(unsigned img_height, unsigned img_width, unsigned block_width,
+                                              unsigned n_blur_samples, const int32_t *gaussian_ids_sorted,
+                                              const int32_t *tile_bins, const void *packed, float rolling_shutter_time,
+                                              float exposure_time, const float *background, const int32_t *status,
+                                              float *out_img, float *final_Ts, int32_t *final_idx, float *out_alpha,
+                                              void *stream);
+B200_API int b200_set_record_colors(int num_points, const float *colors, void *packed, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,3 +116,92 @@ def test_single_process_trainer_matches_manual_adam():
     nz = g != 0
     assert torch.allclose(moved[nz], -1e-2 * torch.sign(g[nz]), atol=1e-6)
     assert (moved[~nz] == 0).all()
+
+
+# ---- PipelinedTrainer (phase A / phase B split, exchange behind the next image's geometry) ---------------------------
+
+def _fake_geometry(model, st, scene, capacity, status):
+    """Stand-in for gsplat.dp.geometry_phase: depends on the geometry rows and the camera only."""
+    p = model.params
+    w = st["cam"][0]
+    geo = (p["means"].sum() * w + torch.sigmoid(p["opacity_logit"]).sum() + p["log_scales"].exp().sum()
+           + (p["quats"] / p["quats"].norm(dim=-1, keepdim=True)).sum())
+    if model.cam_vel is not None:
+        geo = geo + (model.cam_vel.index_select(0, st["cam_index"])[0] * w).sum()
+    if float(w) >= 100.0:  # a camera that "needs more list entries than the capacity": the device would raise the flag
+        status[0] = 1
+    return dict(geo=geo)
+
+
+def _fake_shading(model, geo, scene, target, loss_fn, sh_degree_to_use=3):
+    sh = model.sh_coeffs()
+    rgb = geo["geo"] + sh[:, :1].sum() + (sh[:, 1:] ** 2).sum()
+    img = rgb * torch.ones(scene["H"], scene["W"], 3)
+    loss = loss_fn(img, target)
+    loss.backward()
+    return loss.detach()
+
+
+def _cam_row(w):
+    return torch.tensor([float(w)] + [0.0] * 20)
+
+
+def _pipelined_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, "3dgs-deblur_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsplat import dp, synthetic
+
+    scene = synthetic.make_scene("c1", n_override=50, n_cameras=4)
+    scene.update(fx=1.0, fy=1.0, cx=0.0, cy=0.0)
+    tgt = torch.zeros(scene["H"], scene["W"], 3)
+    # reference: the plain trainer on the same images (same math: averaged gradients, Adam eps 1e-15)
+    dp.render = _fake_render
+    m0 = dp.FlatGaussians(scene, "cpu", n_cameras=4, optimize_velocities=True)
+    t0 = dp.ImageShardedTrainer(m0, scene, lr=1e-2, loss_fn=_torch_l1, optimizer="torch")
+    for step in range(4):
+        i = t0.image_index(step, 4)
+        t0.train_step(dict(w=float(i + 1)), tgt, i)
+    # pipelined trainer, block SH layout, fake phases with the same total function
+    m1 = dp.FlatGaussians(scene, "cpu", n_cameras=4, optimize_velocities=True, sh_layout="block")
+    assert m1.sh_start % 4 == 0 and m1.params["sh"].shape == (50, 16, 3)
+    t1 = dp.PipelinedTrainer(m1, scene, lr=1e-2, loss_fn=_torch_l1, optimizer="torch", geometry_fn=_fake_geometry,
+                             shading_fn=_fake_shading, capacity=1)
+    order = [t0.image_index(s, 4) for s in range(4)]
+    t1.prepare(_cam_row(order[0] + 1), order[0])
+    for step in range(4):
+        nxt = order[step + 1] if step + 1 < 4 else None
+        t1.train_step(tgt, None if nxt is None else _cam_row(nxt + 1), 0 if nxt is None else nxt)
+    t1.finish()
+    for k in ("means", "log_scales", "quats", "opacity_logit"):
+        assert torch.allclose(m0.params[k].detach(), m1.params[k].detach(), rtol=0, atol=1e-6), k
+    assert torch.allclose(m0.cam_vel.detach(), m1.cam_vel.detach(), rtol=0, atol=1e-6)
+    assert torch.allclose(torch.cat((m0.params["sh_dc"], m0.params["sh_rest"]), 1).detach(), m1.params["sh"].detach(), rtol=0, atol=1e-6)
+    gathered = [torch.zeros_like(m1.flat) for _ in range(world)]
+    dist.all_gather(gathered, m1.flat)
+    assert all(torch.equal(gathered[0], g_) for g_ in gathered[1:])  # replicas identical
+    assert float(m1.flat_grad.abs().max()) == 0.0                    # gradients cleared behind the update
+    # veto: ONE rank's image overflows -> the MAX-reduced flag skips the update on EVERY rank, gradients are cleared
+    before = m1.flat.detach().clone()
+    t1.prepare(_cam_row(100.0 if rank == 0 else 1.0), 0)
+    t1.train_step(tgt)
+    t1.finish()
+    assert torch.equal(m1.flat.detach(), before) and float(m1.flat_grad.abs().max()) == 0.0
+    assert t1.vetoed == [4] and int(t1.flag[0]) == 0
+    # and the step after it applies again
+    t1.prepare(_cam_row(1.0), 0)
+    t1.train_step(tgt)
+    t1.finish()
+    assert not torch.equal(m1.flat.detach(), before)
+    if rank == 0:
+        torch.save(m1.flat.clone(), out)
+    dist.destroy_process_group()
+
+
+def test_pipelined_trainer_gloo(tmp_path):
+    """world 2: the pipelined trainer (geometry phase of image k+1 issued before the SH slice of step k is updated) ends
+    at the same parameters as the plain trainer, replicas stay identical, and an overflow on one rank vetoes the step on
+    all of them."""
+    out = str(tmp_path / "flat2.pt")
+    mp.spawn(_pipelined_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.isfinite(torch.load(out)).all()
