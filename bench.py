@@ -79,6 +79,10 @@ def parse():
     ap.add_argument("--sh-chunks", type=int, default=1, help="pieces of the SH block in the gradient exchange (N > 1)")
     ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"], help="FlatAdam kernel or torch's fused Adam")
     ap.add_argument("--no-fused-path", action="store_true", help="skip the extra fused-operator measurement")
+    ap.add_argument("--trainer", default="pipelined", choices=["pipelined", "sync"],
+                    help="pipelined = gsplat.dp.PipelinedTrainer (no host sync, CUDA graphs, exchange behind the next image's "
+                         "geometry); sync = gsplat.dp.ImageShardedTrainer (round-1 path: one host sync per step, eager)")
+    ap.add_argument("--no-graphs", action="store_true", help="pipelined trainer without CUDA-graph capture (debug / A-B)")
     ap.add_argument("--fused", action="store_true",
                     help="render through gsplat.fused.render_gaussians (caller-modified 'next' path) instead of the drop-in operators")
     return ap.parse_args()
@@ -283,13 +287,41 @@ def run_gpu_arm(args):
     cams = make_cameras(scene_dev, dev, not args.no_vel_grad)
     targets = [t.to(dev).float() / 255 for t in targets_u8]
     vel_grad = not args.no_vel_grad
-    model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
     loss_fn = None
     if args.loss == "photometric":
         from gsplat.losses import photometric_loss as loss_fn
-    trainer = ImageShardedTrainer(model, scene_dev, lr=1e-4, fused=args.fused, sh_chunks=args.sh_chunks, optimizer=args.optimizer,
-                                  loss_fn=loss_fn)
+    pipelined = args.trainer == "pipelined" and not args.fused
     H, W, S, N = scene["H"], scene["W"], scene["blur_samples"], scene["N"]
+    cam_rows = [torch.cat([c["viewmat"].reshape(-1), c["lin_vel"], c["ang_vel"], c["cam_pos"]]).contiguous() for c in cams]  # device
+    if pipelined:
+        from gsplat.dp import PipelinedTrainer
+
+        scene_dev.update(fx=cams[0]["fx"], fy=cams[0]["fy"], cx=cams[0]["cx"], cy=cams[0]["cy"])
+        model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad, sh_layout="block")
+        trainer = PipelinedTrainer(model, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs)
+    else:
+        model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
+        trainer = ImageShardedTrainer(model, scene_dev, lr=1e-4, fused=args.fused, sh_chunks=args.sh_chunks, optimizer=args.optimizer,
+                                      loss_fn=loss_fn)
+
+    class Stepper:
+        """step(k): one train step on image k % n_img (consecutive k: the pipelined trainer stages image k+1 inside step k)."""
+
+        def __init__(self, images, cam_source):
+            self.images, self.cam_source, self.staged = images, cam_source, None
+
+        def step(self, k, image=None):
+            i = k % n_img
+            tgt = self.images[i] if image is None else image
+            if not pipelined:
+                return trainer.train_step(cams[i] if self.cam_source is None else self.cam_source(i), tgt, i)
+            if self.staged != k:
+                trainer.prepare(cam_rows[i] if self.cam_source is None else self.cam_source(i), i)
+            nxt = (k + 1) % n_img
+            self.staged = k + 1
+            return trainer.train_step(tgt, cam_rows[nxt] if self.cam_source is None else self.cam_source(nxt), nxt)
+
+    stepper = Stepper(targets, None)
 
     def barrier():
         if world > 1:
@@ -299,9 +331,9 @@ def run_gpu_arm(args):
     # ---- kernel-resident metric: inputs already in HBM, CUDA-event timing, max over ranks
     # warm-up: at least one pass over every training image, so no timed step meets a new camera (first-use allocations,
     # list capacities) -- args.warmup is a lower bound
-    n_warm = max(args.warmup, n_img + 2)
+    n_warm = max(args.warmup, n_img + 4)  # (+ the two eager rounds before the pipelined trainer captures its graphs)
     for w in range(n_warm):
-        trainer.train_step(cams[w % n_img], targets[w % n_img], w % n_img)
+        stepper.step(w)
     # the clock sampler forks nvidia-smi: start it BEFORE the barrier that opens the timed region (round 1 started it
     # on rank 0 after the barrier, so the other ranks waited for rank 0's fork/exec inside their first allreduce and
     # that latency was charged to the max-over-ranks time)
@@ -315,8 +347,9 @@ def run_gpu_arm(args):
     l0 = lib.b200_launch_count()
     evs[0].record()
     for k in range(args.steps):
-        i = k % n_img
-        trainer.train_step(cams[i], targets[i], i)
+        stepper.step(n_warm + k)
+        if pipelined and k == args.steps - 1:
+            trainer.finish()  # the last step's SH update (side stream) belongs to the timed region
         evs[k + 1].record()
     barrier()
     launches = (lib.b200_launch_count() - l0) / args.steps
@@ -361,8 +394,9 @@ def run_gpu_arm(args):
 
         nprof = 20
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            k0 = stepper.staged if (pipelined and stepper.staged is not None) else 0
             for k in range(nprof):
-                trainer.train_step(cams[k % n_img], targets[k % n_img], k % n_img)
+                stepper.step(k0 + k)
             torch.cuda.synchronize()
         dev_us = sum(e.device_time_total for e in prof.key_averages())
         gpu_busy = {"kernel_ms_per_step": dev_us / nprof / 1000.0, "note": "sum of device time of every kernel in a step (CUPTI); "
@@ -401,19 +435,27 @@ def run_gpu_arm(args):
     loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_done = [torch.cuda.Event() for _ in range(2)]
 
+    # the pipelined trainer takes the uint8 image as it arrives (the conversion is the first node of its B graph) and the
+    # NEXT image's camera row straight from pinned host memory (84 bytes H2D inside its step)
+    e2e_stepper = Stepper(None, (lambda i: cam_host[i]) if pipelined else None)
+
     def e2e_loop(n_steps):
         losses = []
         prefetcher.start(0)
+        e2e_stepper.staged = None
         for k in range(n_steps):
             b, i = k % 2, k % n_img
             img_u8, ch = prefetcher.get(next_index=(k + 1) % n_img)
-            tgt = img_u8.float() / 255
-            cam = dict(cams[i], viewmat=ch[:12].view(3, 4), lin_vel=ch[12:15], ang_vel=ch[15:18], vel0=ch[12:18], cam_pos=ch[18:21])
-            loss = trainer.train_step(cam, tgt, i)
+            if pipelined:
+                loss = e2e_stepper.step(k, image=img_u8)
+            else:
+                tgt = img_u8.float() / 255
+                cam = dict(cams[i], viewmat=ch[:12].view(3, 4), lin_vel=ch[12:15], ang_vel=ch[15:18], vel0=ch[12:18], cam_pos=ch[18:21])
+                loss = trainer.train_step(cam, tgt, i)
             prefetcher.done()
             loss_host[b].copy_(loss.detach().reshape(1), non_blocking=True)  # loss D2H (4 bytes) every step
             loss_done[b].record(main_stream)
-            if k > 0:  # read the previous step's loss: it completed before this step's intersect-count sync
+            if k > 0:  # read the previous step's loss while this step is queued / running
                 loss_done[1 - b].synchronize()
                 losses.append(float(loss_host[1 - b][0]))
         loss_done[(n_steps - 1) % 2].synchronize()
@@ -421,7 +463,7 @@ def run_gpu_arm(args):
         assert all(x == x for x in losses)  # no NaNs, and every step's loss reached the host
         return losses
 
-    e2e_loop(4)
+    e2e_loop(max(4, n_img + 4))  # (first use of the uint8 targets: two eager rounds, then graph capture)
     barrier()
     t0 = time.perf_counter()
     e2e_loop(e2e_steps)
@@ -434,7 +476,13 @@ def run_gpu_arm(args):
     h2d = prefetcher.bytes_per_step
     e2e = {"value": world * 1000.0 / e2e_ms, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4 + 8, "steps": e2e_steps,
-           "path": "gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians via gsplat.dp.ImageShardedTrainer"}
+           "path": "gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians via gsplat.dp." + (
+               "PipelinedTrainer" if pipelined else "ImageShardedTrainer")}
+    trainer_status = None
+    if pipelined:
+        trainer.finish()
+        trainer_status = trainer.sync_status()
+        trainer_status["graphs"] = sum(1 for e in trainer._graphs.values() if e["gA"] is not None and e["gB"] is not None)
 
     # ---- per-kernel timing + roofline of the dominant kernel (rank 0), CUDA events on the launch stream
     kernels, roofline = {}, None
@@ -450,7 +498,7 @@ def run_gpu_arm(args):
                          None, scene["rolling_shutter_time"], scene["exposure_time"], cam["viewmat"], cam["fx"], cam["fy"],
                          cam["cx"], cam["cy"], H, W, 16, 0.01)
             cov3d, xys, depths, pix_vels, radii, conics, comp, nth = _C.project_gaussians_forward(*args_proj, _vel_tensors=(lin, ang))
-            coeffs = torch.cat((p["sh_dc"], p["sh_rest"]), dim=1).contiguous()
+            coeffs = model.sh_coeffs().detach().contiguous()
             dirs = (p["means"] - cam["cam_pos"]).contiguous()
             colors = torch.clamp(_C.compute_sh_forward("fast", N, 3, 3, dirs, coeffs) + 0.5, min=0).contiguous()
             opac = (torch.sigmoid(p["opacity_logit"]) * comp[:, None]).contiguous()
@@ -562,11 +610,15 @@ def run_gpu_arm(args):
         "data": "synthetic", "warmup_run": n_warm,
         "config": bench_config(args.config, N, W, H, S),
         "details": {"step": "project+SH+bin/sort+blend fwd, L1 (gsplat.losses.l1_loss), full bwd, grad allreduce (N>1), Adam over the flat buffer; 1 image per GPU per step",
-                    "optimizer": "gsplat.optim.FlatAdam (b200_adam_step)" if args.optimizer == "b200" else "torch.optim.Adam(fused=True)",
+                    "optimizer": "gsplat.optim.FlatAdam (device step state)" if pipelined else ("gsplat.optim.FlatAdam (b200_adam_step)" if args.optimizer == "b200" else "torch.optim.Adam(fused=True)"),
                     "sh_chunks": args.sh_chunks, "loss": args.loss, "velocity_grad": vel_grad, "global_batch": world,
                     "api": ("gsplat.fused.render_gaussians (raw parameters, caller-modified)" if args.fused else
                             "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians"),
-                    "parallelism": f"image-sharded dp{world}"},
+                    "parallelism": f"image-sharded dp{world}",
+                    "trainer": ("gsplat.dp.PipelinedTrainer: no host sync (capacity-mode tile lists, device-side veto), two CUDA "
+                                "graphs per step, gradient exchange + SH update behind the next image's projection/binning"
+                                if pipelined else "gsplat.dp.ImageShardedTrainer (one host sync per step, eager launches)"),
+                    "trainer_status": trainer_status},
         "step_ms": step_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
