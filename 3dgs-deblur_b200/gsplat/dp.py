@@ -407,6 +407,11 @@ class PipelinedTrainer:
         else:
             raise ValueError("optimizer must be 'b200' or 'torch'")
         if self.cuda:
+            # Everything this trainer queues runs on its own stream `main` (callers on another stream are ordered before /
+            # after each call).  Autograd ties every leaf's gradient accumulation to the stream that was current when the
+            # accumulator was first used; if that were the legacy default stream, the backward pass inside a graph capture
+            # would have to synchronise with it, which invalidates the capture.
+            self.main = torch.cuda.Stream(device=dev)
             self.side = torch.cuda.Stream(device=dev)
             self.ev_prepared, self.ev_sh_done = torch.cuda.Event(), torch.cuda.Event()
             self._host_words = torch.zeros(2, 24, dtype=torch.int32).pin_memory()   # status (4) | adam state (16) | quat flag
@@ -470,7 +475,7 @@ class PipelinedTrainer:
             return
         if self.use_graphs and e["warm"] >= 2:  # two eager warm-up rounds (allocator, lazy inits), then capture
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.main):
                 e["geo"] = self.geometry_fn(self.model, self.st, self.scene, self.capacity, self.status)
             e["gA"] = g
             g.replay()  # (capture does not execute)
@@ -489,7 +494,7 @@ class PipelinedTrainer:
             e["target"] = torch.empty_like(target)
             e["target"].copy_(target)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.main):
                 tgt = e["target"].float() / 255 if e["target"].dtype == torch.uint8 else e["target"]
                 self.loss.copy_(self.shading_fn(self.model, e["geo"], self.scene, tgt, self.loss_fn, self.sh_degree))
             e["gB"] = g
@@ -500,9 +505,35 @@ class PipelinedTrainer:
         e["warm"] += 1
 
     # ---- public API ----------------------------------------------------------------------------------------------
+    class _OnMain:
+        """Run a block on the trainer's stream, ordered after the caller's current stream and before its later work."""
+
+        def __init__(self, tr):
+            self.tr, self.ctx, self.cur = tr, None, None
+
+        def __enter__(self):
+            tr = self.tr
+            if not tr.cuda:
+                return
+            self.cur = torch.cuda.current_stream(tr.device)
+            if self.cur != tr.main:
+                tr.main.wait_stream(self.cur)
+                self.ctx = torch.cuda.stream(tr.main)
+                self.ctx.__enter__()
+
+        def __exit__(self, *exc):
+            if self.ctx is not None:
+                self.ctx.__exit__(*exc)
+                self.cur.wait_stream(self.tr.main)
+            return False
+
     def prepare(self, cam, cam_index: int = 0):
         """Stage the camera of the image the next train_step trains on (phase A itself is queued by train_step: at once
         for the first image, behind the previous step's geometry update afterwards)."""
+        with self._OnMain(self):
+            self._prepare(cam, cam_index)
+
+    def _prepare(self, cam, cam_index):
         self._set_camera(cam, cam_index)
         self._size_capacity()
         self._prepared = True
@@ -519,6 +550,10 @@ class PipelinedTrainer:
         """Trains on the prepared image (B, exchange, update) and, given `next_cam`, runs A for the next image while the
         SH block is still being exchanged / updated.  Returns the device loss (a static tensor: copy it if you keep it)."""
         assert getattr(self, "_prepared", False), "call prepare(cam, cam_index) before the first train_step"
+        with self._OnMain(self):
+            return self._train_step(target, next_cam, next_index)
+
+    def _train_step(self, target, next_cam, next_index):
         m = self.model
         e = self._entry((tuple(target.shape), target.dtype))
         self._ensure_A(e)
@@ -550,7 +585,7 @@ class PipelinedTrainer:
         # ---- next image's geometry (needs only the rows just updated), SH update beside it
         self._prepared = False
         if next_cam is not None:
-            self.prepare(next_cam, next_index)
+            self._prepare(next_cam, next_index)
         if self.cuda:
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_prepared)
@@ -580,10 +615,12 @@ class PipelinedTrainer:
         g.zero_()
 
     def finish(self):
-        """Drain the side stream (call before reading parameters)."""
-        if self.cuda and self._pending_sh is not None:
-            torch.cuda.current_stream().wait_event(self.ev_sh_done)
-            self._pending_sh = None
+        """Order the caller's stream after everything queued so far, the SH update on the side stream included (call
+        before reading parameters)."""
+        with self._OnMain(self):
+            if self.cuda and self._pending_sh is not None:
+                torch.cuda.current_stream().wait_event(self.ev_sh_done)
+                self._pending_sh = None
 
     # ---- lagged host view of the device status (overflow / vetoes / input check) ---------------------------------
     def _poll_host(self):
@@ -628,6 +665,5 @@ class PipelinedTrainer:
                 if self._host_seen[slot]:
                     self._consume(self._host_words[slot])
                     self._host_seen[slot] = False
-            w = torch.cat([self.status, self.adam.state]).tolist()
-            self._consume(w + [0] * 4)
+            self._consume(torch.cat([self.status, self.adam.state, torch.zeros(4, dtype=torch.int32, device=self.device)]).cpu())
         return dict(entries_max=int(self.status[2]), capacity=self.capacity, vetoed=list(self.vetoed), steps=self.steps)
