@@ -81,8 +81,27 @@ class FlatGaussians:
         assert off == total
         self.sh_start = self.slices["sh_dc"][0]  # flat[sh_start:] = all SH coefficients
         self.floats_per_gaussian = sum(widths.values())
-        if sh_layout == "block":  # read-only conveniences for code written against Splatfacto's two tensors
-            self.views = {"sh_dc": self.params["sh"][:, :1], "sh_rest": self.params["sh"][:, 1:]}
+
+    @property
+    def views(self) -> Dict[str, torch.Tensor]:
+        """Block layout: Splatfacto's two SH tensors as read-only (detached) views of the one block."""
+        sh = self.params["sh"].detach()
+        return {"sh_dc": sh[:, :1], "sh_rest": sh[:, 1:]}
+
+    def rebind_leaves(self):
+        """Replace every parameter by a fresh leaf tensor over the same storage (same .grad views).  Autograd ties a
+        leaf's gradient accumulator to the stream that is current when the accumulator is first created; a trainer that
+        captures its backward pass into a CUDA graph on its own stream calls this (on that stream) so that no accumulator
+        made earlier on the legacy default stream forces the capture to synchronise with it."""
+        for name in list(self.params):
+            old = self.params[name]
+            new = old.detach().requires_grad_(True)
+            new.grad = old.grad
+            self.params[name] = new
+        if self.cam_vel is not None:
+            new = self.cam_vel.detach().requires_grad_(True)
+            new.grad = self.cam_vel.grad
+            self.cam_vel = new
 
     def sh_coeffs(self) -> torch.Tensor:
         """(N, K, 3) coefficients as spherical_harmonics wants them."""
@@ -413,6 +432,7 @@ class PipelinedTrainer:
             # would have to synchronise with it, which invalidates the capture.
             self.main = torch.cuda.Stream(device=dev)
             self.side = torch.cuda.Stream(device=dev)
+            model.rebind_leaves()  # gradient accumulators are (re)created on `main` by the first step
             self.ev_prepared, self.ev_sh_done = torch.cuda.Event(), torch.cuda.Event()
             self._host_words = torch.zeros(2, 24, dtype=torch.int32).pin_memory()   # status (4) | adam state (16) | quat flag
             self._host_ev = [torch.cuda.Event(), torch.cuda.Event()]
