@@ -406,6 +406,8 @@ class PipelinedTrainer:
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.capacity = capacity
         self.vetoed: List[int] = []     # step indices whose update was skipped (the caller repeats those images)
+        self.graph_kernel_launches = 0  # libb200splat kernels replayed from captured graphs (the C launch counter only
+        #                                 sees launches made through the C ABI, i.e. eager ones and those DURING capture)
         self.steps = 0
         self._geo = None
         self._graphs: Dict[tuple, Dict] = {}
@@ -488,16 +490,22 @@ class PipelinedTrainer:
             e = self._graphs[key] = dict(gA=None, gB=None, geo=None, target=None, warm=0)
         return e
 
+    def _lib_launches(self):
+        from gsplat import _lib
+        return _lib.load().b200_launch_count() if self.cuda else 0
+
     def _run_A(self, e):
         if self.use_graphs and e["gA"] is not None:
             e["gA"].replay()
+            self.graph_kernel_launches += e["nA"]
             self._geo = e["geo"]
             return
         if self.use_graphs and e["warm"] >= 2:  # two eager warm-up rounds (allocator, lazy inits), then capture
             g = torch.cuda.CUDAGraph()
+            n0 = self._lib_launches()
             with torch.cuda.graph(g, stream=self.main):
                 e["geo"] = self.geometry_fn(self.model, self.st, self.scene, self.capacity, self.status)
-            e["gA"] = g
+            e["gA"], e["nA"] = g, self._lib_launches() - n0   # libb200splat kernels recorded in the graph
             g.replay()  # (capture does not execute)
             self._geo = e["geo"]
             return
@@ -508,16 +516,18 @@ class PipelinedTrainer:
         if self.use_graphs and e["gB"] is not None:
             e["target"].copy_(target, non_blocking=True)
             e["gB"].replay()
+            self.graph_kernel_launches += e["nB"]
             return
         if self.use_graphs and e["gA"] is not None and e["warm"] >= 2:
             # B is captured against the tensors A's graph writes (static addresses), with a static target buffer
             e["target"] = torch.empty_like(target)
             e["target"].copy_(target)
             g = torch.cuda.CUDAGraph()
+            n0 = self._lib_launches()
             with torch.cuda.graph(g, stream=self.main):
                 tgt = e["target"].float() / 255 if e["target"].dtype == torch.uint8 else e["target"]
                 self.loss.copy_(self.shading_fn(self.model, e["geo"], self.scene, tgt, self.loss_fn, self.sh_degree))
-            e["gB"] = g
+            e["gB"], e["nB"] = g, self._lib_launches() - n0
             g.replay()
             return
         tgt = target.float() / 255 if target.dtype == torch.uint8 else target

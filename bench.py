@@ -345,7 +345,7 @@ def run_gpu_arm(args):
     barrier()
     # one event per step boundary: total = last - first (what `value` uses), per-step spread shows one-off stalls
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    l0 = lib.b200_launch_count()
+    l0 = lib.b200_launch_count() + (trainer.graph_kernel_launches if pipelined else 0)
     evs[0].record()
     for k in range(args.steps):
         stepper.step(n_warm + k)
@@ -353,7 +353,7 @@ def run_gpu_arm(args):
             trainer.finish()  # the last step's SH update (side stream) belongs to the timed region
         evs[k + 1].record()
     barrier()
-    launches = (lib.b200_launch_count() - l0) / args.steps
+    launches = (lib.b200_launch_count() + (trainer.graph_kernel_launches if pipelined else 0) - l0) / args.steps
     ms = evs[0].elapsed_time(evs[-1]) / args.steps
     per_step = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps))
     clocks = sampler.stop() if rank == 0 else None
