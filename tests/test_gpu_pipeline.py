@@ -220,8 +220,8 @@ def test_pipelined_trainer_vetoes_an_overflowing_image_and_recovers():
     t.train_step(cams[0]["target"])
     t.finish()
     need = t.sync_status()["entries_max"]
-    assert need > 4096
-    t.capacity = 4096  # far too small
+    assert need > 1024
+    t.capacity = need // 4  # far too small
     before = m.flat.detach().clone()
     t.prepare(cams[1], 1)
     t.train_step(cams[1]["target"])
