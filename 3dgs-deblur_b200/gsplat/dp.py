@@ -381,7 +381,7 @@ class PipelinedTrainer:
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, loss_fn=None, use_graphs: bool = True,
                  capacity: Optional[int] = None, sh_degree_to_use: int = 3, geometry_fn=None, shading_fn=None,
-                 optimizer: str = "b200"):
+                 optimizer: str = "b200", sh_chunks: int = 2):
         self.model, self.scene = model, dict(scene)
         if loss_fn is None:
             from gsplat.losses import l1_loss as loss_fn
@@ -414,6 +414,11 @@ class PipelinedTrainer:
         self._flag_work = None
         self._pending_sh = None
         self.optimizer = optimizer
+        # the SH block is exchanged in `sh_chunks` pieces so that the update of piece i runs while piece i+1 is on the wire
+        lo, total = model.sh_start, model.flat.numel()
+        n_sh = max(1, int(sh_chunks)) if self.distributed else 1
+        cuts = [lo + ((total - lo) * k // n_sh) // 4 * 4 for k in range(n_sh)] + [total]
+        self._sh_bounds = [(cuts[k], cuts[k + 1]) for k in range(n_sh) if cuts[k + 1] > cuts[k]]
         if optimizer == "b200":
             from gsplat.optim import FlatAdam
             self.adam = FlatAdam(model.flat, model.flat_grad, lr=lr, eps=1e-15).use_device_state()
@@ -594,8 +599,8 @@ class PipelinedTrainer:
         lo, total = m.sh_start, m.flat.numel()
         works = None
         if self.distributed:
-            works = [dist.all_reduce(m.flat_grad[:lo], op=self._op, group=self.group, async_op=True),
-                     dist.all_reduce(m.flat_grad[lo:], op=self._op, group=self.group, async_op=True)]
+            works = [dist.all_reduce(m.flat_grad[:lo], op=self._op, group=self.group, async_op=True)]
+            works += [dist.all_reduce(m.flat_grad[a:b_], op=self._op, group=self.group, async_op=True) for a, b_ in self._sh_bounds]
             self._flag_work.wait()
         scale = 1.0 if (self._avg or not self.distributed) else 1.0 / self.world
         veto_host = False
@@ -619,16 +624,18 @@ class PipelinedTrainer:
         if self.cuda:
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_prepared)
-                if works is not None:
-                    works[1].wait()
-                self._update(lo, total, scale, veto_host, 1)
+                for j, (a, b_) in enumerate(self._sh_bounds):
+                    if works is not None:
+                        works[1 + j].wait()
+                    self._update(a, b_, scale, veto_host, 1)
                 self.ev_sh_done.record(self.side)
             self._pending_sh = True
             if next_cam is not None:
                 self._ensure_A(self._entry((tuple(target.shape), target.dtype)))
         else:
-            if works is not None:
-                works[1].wait()
+            for j in range(len(self._sh_bounds)):
+                if works is not None:
+                    works[1 + j].wait()
             self._update(lo, total, scale, veto_host, 1)
         self.steps += 1
         return self.loss
