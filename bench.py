@@ -79,6 +79,12 @@ def parse():
     ap.add_argument("--sh-chunks", type=int, default=1, help="pieces of the SH block in the gradient exchange (N > 1)")
     ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"], help="FlatAdam kernel or torch's fused Adam")
     ap.add_argument("--no-fused-path", action="store_true", help="skip the extra fused-operator measurement")
+    ap.add_argument("--mode", default="image", choices=["image", "scene"],
+                    help="image = every rank renders another image of ONE scene, one gradient exchange per step (BASELINE configs "
+                         "2-5); scene = whole scenes shard across the GPUs (BASELINE config 5: `--config c5 --mode scene`): rank r "
+                         "trains scene r mod --scenes, ranks that share a scene form an image-sharded group, no exchange between scenes")
+    ap.add_argument("--scenes", type=int, default=5, help="number of independent scenes in --mode scene")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-kernel measurements (ref_gpu key)")
     ap.add_argument("--trainer", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined = gsplat.dp.PipelinedTrainer (no host sync, CUDA graphs, exchange behind the next image's "
                          "geometry); sync = gsplat.dp.ImageShardedTrainer (round-1 path: one host sync per step, eager)")
@@ -261,6 +267,57 @@ def make_cameras(scene, device, optimize_vel):
     return cams
 
 
+def measure_ref_gpu(args, scene_dev, cams, targets, n_img, value, loss_fn, dev):
+    """`ref_gpu`: train-step images/s of the UNMODIFIED reference gsplat CUDA kernels (oracle/_ref) on this arm's
+    workload, three ways, plus this repo on the zero-motion variant so the ratio without the reference's phantom-tile-0
+    tail is visible.  Reported beside the arm's value; never part of a timed region of the arm."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import build_ref
+        import ref_bench
+
+        if not os.path.exists(build_ref.so_path()):
+            return {"unavailable": "oracle/_ref/gsplat_ref_csrc.so not built (needs /root/reference at build time)"}
+        out = {"kernels": "unmodified reference CUDA extension (forward.cu / backward.cu / bindings.cu, -O3 --use_fast_math, sm_100), "
+                          "driven with the reference's own op sequence (oracle/ref_ops.py), torch L1 + torch fused Adam"}
+        out["cuda_projection"] = ref_bench.measure(args.config, args.n, n_img, 30, 5, "cuda", breakdown=True)
+        out["torch_projection_velocity_grad"] = ref_bench.measure(args.config, args.n, n_img, 20, 3, "torch")
+        out["static_zero_velocity"] = ref_bench.measure(args.config, args.n, n_img, 30, 5, "static")
+        # this repo on the zero-velocity variant (same trainer as the arm)
+        from gsplat.dp import FlatGaussians, PipelinedTrainer
+
+        rows0 = []
+        for c in cams:
+            z = torch.zeros(3, device=dev)
+            rows0.append(torch.cat([c["viewmat"].reshape(-1), z, z, c["cam_pos"]]).contiguous())
+        m0 = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=True, sh_layout="block")
+        t0 = PipelinedTrainer(m0, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs)
+        t0.prepare(rows0[0], 0)
+        n_w, n_t = n_img + 4, 60
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for k in range(n_w + n_t):
+            if k == n_w:
+                t0.finish()
+                e0.record()
+            t0.train_step(targets[k % n_img], rows0[(k + 1) % n_img], (k + 1) % n_img)
+        t0.finish()
+        e1.record()
+        torch.cuda.synchronize()
+        ms0 = e0.elapsed_time(e1) / n_t
+        out["this_repo_static_zero_velocity"] = {"value": 1000.0 / ms0, "unit": "images/s", "ms_per_step": ms0, "steps": n_t}
+        out["ratio_vs_cuda_projection"] = round(value / out["cuda_projection"]["value"], 2)
+        out["ratio_vs_torch_projection"] = round(value / out["torch_projection_velocity_grad"]["value"], 2)
+        out["ratio_static"] = round(out["this_repo_static_zero_velocity"]["value"] / out["static_zero_velocity"]["value"], 2)
+        out["note"] = ("ratios = this arm's `value` (velocities carry gradients) / the reference variant; `torch_projection` is what "
+                       "train.py runs by default (velocity optimisation on: project_gaussians.py:81-112), timed through "
+                       "oracle/torch_oracle.py's restatement of _torch_impl.project_gaussians_forward")
+        return out
+    except Exception as e:  # a reported comparator, never a reason to lose the arm's line
+        return {"unavailable": repr(e)[:300]}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -278,9 +335,19 @@ def run_gpu_arm(args):
 
     lib = _lib.load()
     n_img = args.images
-    # the same scene (parameters) on every rank; rank r trains on its own cameras / images
-    scene = synthetic.make_scene(args.config, device="cpu", n_override=args.n, n_cameras=n_img * world)
-    my = [scene["cameras"][i * world + rank] for i in range(n_img)]
+    # image mode: the same scene (parameters) on every rank; rank r trains on its own cameras / images.
+    # scene mode: rank r holds scene r mod S; the ranks of one scene form its (image-sharded) group, groups never talk.
+    group, gworld, grank, scene_id = None, world, rank, 0
+    if args.mode == "scene":
+        n_sc = max(1, min(args.scenes, world))
+        scene_id = rank % n_sc
+        members = [r for r in range(world) if r % n_sc == scene_id]
+        gworld, grank = len(members), members.index(rank)
+        if world > 1:
+            groups = [dist.new_group([r for r in range(world) if r % n_sc == s_]) for s_ in range(n_sc)]  # (collective: every rank creates every group)
+            group = groups[scene_id]
+    scene = synthetic.make_scene(args.config, device="cpu", n_override=args.n, n_cameras=n_img * gworld, seed_offset=100 * scene_id)
+    my = [scene["cameras"][i * gworld + grank] for i in range(n_img)]
     targets_u8 = [(c["target"] * 255).to(torch.uint8).contiguous().pin_memory() for c in my]
     scene_dev = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in scene.items() if k != "cameras"}
     scene_dev["cameras"] = my
@@ -298,12 +365,12 @@ def run_gpu_arm(args):
 
         scene_dev.update(fx=cams[0]["fx"], fy=cams[0]["fy"], cx=cams[0]["cx"], cy=cams[0]["cy"])
         model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad, sh_layout="block")
-        trainer = PipelinedTrainer(model, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs)
+        trainer = PipelinedTrainer(model, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs, group=group)
         torch.cuda.set_stream(trainer.main)  # everything below (events, prefetcher, timing) runs on the trainer's stream
     else:
         model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
         trainer = ImageShardedTrainer(model, scene_dev, lr=1e-4, fused=args.fused, sh_chunks=args.sh_chunks, optimizer=args.optimizer,
-                                      loss_fn=loss_fn)
+                                      loss_fn=loss_fn, group=group)
 
     class Stepper:
         """step(k): one train step on image k % n_img (consecutive k: the pipelined trainer stages image k+1 inside step k)."""
@@ -595,6 +662,12 @@ def run_gpu_arm(args):
                         "note": "blend kernels are FP32-issue / MUFU / SHFL / atomic bound, not HBM bound (SURVEY 0.5); see `issue`",
                         "intersections": I, "culled_list_entries": M, "visible": V}
 
+    # ---- the comparator north_star names: the reference's own gsplat CUDA kernels (oracle/_ref = the unmodified extension
+    # built by oracle/build_ref.py) on the same workload, same GPU, outside every timed region of this arm
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_ref_gpu and not args.fused:
+        ref_gpu = measure_ref_gpu(args, scene_dev, cams, targets, n_img, value, loss_fn, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -615,7 +688,9 @@ def run_gpu_arm(args):
                     "sh_chunks": args.sh_chunks, "loss": args.loss, "velocity_grad": vel_grad, "global_batch": world,
                     "api": ("gsplat.fused.render_gaussians (raw parameters, caller-modified)" if args.fused else
                             "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians"),
-                    "parallelism": f"image-sharded dp{world}",
+                    "parallelism": (f"image-sharded dp{world}" if args.mode == "image" else
+                                    f"scene-sharded: {min(args.scenes, world)} independent scenes over {world} GPUs "
+                                    f"(groups of {world // min(args.scenes, world)}-{-(-world // min(args.scenes, world))} ranks per scene, image-sharded inside a group)"),
                     "trainer": ("gsplat.dp.PipelinedTrainer: no host sync (capacity-mode tile lists, device-side veto), two CUDA "
                                 "graphs per step, gradient exchange + SH update behind the next image's projection/binning"
                                 if pipelined else "gsplat.dp.ImageShardedTrainer (one host sync per step, eager launches)"),
@@ -623,6 +698,8 @@ def run_gpu_arm(args):
         "step_ms": step_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
+    if ref_gpu:
+        out["ref_gpu"] = ref_gpu
     if fused_path:
         out["fused_path"] = fused_path
     if gpu_busy:

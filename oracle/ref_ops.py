@@ -90,15 +90,34 @@ class RefRasterize(torch.autograd.Function):
         return (v_xy, None, v_pix, None, v_conic, None, v_colors, v_opac) + (None,) * 7
 
 
-def render(model, cam, scene):
-    """The Splatfacto render block on the reference kernels (mirror of gsplat.dp.render)."""
+def project_torch_path(means3d, scales, quats, lin, ang, rs, exposure, viewmat, fx, fy, cx, cy, H, W, bw):
+    """The reference's projection when a camera velocity requires grad -- train.py's default (train.py:64-67): it leaves
+    CUDA for ~60 PyTorch ops + autograd (project_gaussians.py:81-112 -> _torch_impl.py:396-467).  /root/reference cannot
+    travel to the GPU box, so this drives oracle/torch_oracle.py, the restatement of that function that
+    tests/test_oracle_golden.py pins against the reference's own outputs (same op sequence, same boolean-mask outputs)."""
+    import torch_oracle as TO
+
+    vm4 = torch.cat([viewmat.reshape(3, 4), torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=viewmat.device)], 0)  # project_gaussians.py:84
+    o = TO.project(means3d, scales, 1.0, quats, lin.reshape(-1), ang.reshape(-1), rs, exposure, vm4, fx, fy, cx, cy, H, W, bw)
+    return (o["xys"].contiguous(), o["depths"].contiguous(), o["pix_vels"].contiguous(), o["radii"].to(torch.int32).contiguous(),
+            o["conics"].contiguous(), o["compensation"].contiguous(), o["num_tiles_hit"].to(torch.int32).contiguous(), None)
+
+
+def render(model, cam, scene, torch_projection=False):
+    """The Splatfacto render block on the reference kernels (mirror of gsplat.dp.render).  torch_projection: velocities
+    carry gradients, so the projection runs the reference's PyTorch path instead of its CUDA kernel."""
     p = model.params
     H, W, bw = scene["H"], scene["W"], scene["block_width"]
     quats = p["quats"] / p["quats"].norm(dim=-1, keepdim=True)
     assert (quats.norm(dim=-1) - 1 < 1e-6).all()  # project_gaussians.py:69
-    xys, depths, pix_vels, radii, conics, comp, nth, _ = RefProject.apply(
-        p["means"], torch.exp(p["log_scales"]), 1.0, quats, cam["lin_vel"], cam["ang_vel"], scene["rolling_shutter_time"],
-        scene["exposure_time"], cam["viewmat"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, bw, 0.01)
+    if torch_projection:
+        xys, depths, pix_vels, radii, conics, comp, nth, _ = project_torch_path(
+            p["means"], torch.exp(p["log_scales"]), quats, cam["lin_vel"], cam["ang_vel"], scene["rolling_shutter_time"],
+            scene["exposure_time"], cam["viewmat"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, bw)
+    else:
+        xys, depths, pix_vels, radii, conics, comp, nth, _ = RefProject.apply(
+            p["means"], torch.exp(p["log_scales"]), 1.0, quats, cam["lin_vel"], cam["ang_vel"], scene["rolling_shutter_time"],
+            scene["exposure_time"], cam["viewmat"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, bw, 0.01)
     colors = torch.cat((p["sh_dc"], p["sh_rest"]), dim=1)
     viewdirs = (p["means"].detach() - cam["cam_pos"]).contiguous()
     rgbs = torch.clamp(RefSH.apply(3, viewdirs, colors.contiguous()) + 0.5, min=0.0)
