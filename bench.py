@@ -282,9 +282,14 @@ def measure_ref_gpu(args, scene_dev, cams, targets, n_img, value, loss_fn, dev):
             return {"unavailable": "oracle/_ref/gsplat_ref_csrc.so not built (needs /root/reference at build time)"}
         out = {"kernels": "unmodified reference CUDA extension (forward.cu / backward.cu / bindings.cu, -O3 --use_fast_math, sm_100), "
                           "driven with the reference's own op sequence (oracle/ref_ops.py), torch L1 + torch fused Adam"}
-        out["cuda_projection"] = ref_bench.measure(args.config, args.n, n_img, 30, 5, "cuda", breakdown=True)
-        out["torch_projection_velocity_grad"] = ref_bench.measure(args.config, args.n, n_img, 20, 3, "torch")
-        out["static_zero_velocity"] = ref_bench.measure(args.config, args.n, n_img, 30, 5, "static")
+        # the reference extension launches on the legacy default stream (bindings.cu: `<<<grid, block>>>`); torch's side
+        # streams are non-blocking, i.e. NOT ordered against it -- so the reference runs with torch on the default stream too
+        torch.cuda.synchronize()
+        with torch.cuda.stream(torch.cuda.default_stream(dev)):
+            out["cuda_projection"] = ref_bench.measure(args.config, args.n, n_img, 30, 5, "cuda", breakdown=True)
+            out["torch_projection_velocity_grad"] = ref_bench.measure(args.config, args.n, n_img, 20, 3, "torch")
+            out["static_zero_velocity"] = ref_bench.measure(args.config, args.n, n_img, 30, 5, "static")
+        torch.cuda.synchronize()
         # this repo on the zero-velocity variant (same trainer as the arm)
         from gsplat.dp import FlatGaussians, PipelinedTrainer
 
