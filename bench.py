@@ -273,10 +273,16 @@ def measure_ref_gpu(args, scene_dev, cams, targets, n_img, value, loss_fn, dev):
     tail is visible.  Reported beside the arm's value; never part of a timed region of the arm."""
     import torch
 
+    # (oracle/ holds both the package `oracle` and flat helper modules: put the directory on the path only while the
+    # helpers are imported, or a later `from oracle import oracle` would find oracle/oracle.py first)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     try:
         import build_ref
         import ref_bench
+        import ref_ops  # noqa: F401
+        import torch_oracle  # noqa: F401
+        sys.path.remove(os.path.join(ROOT, "oracle"))
+        sys.modules.pop("oracle", None) if not hasattr(sys.modules.get("oracle"), "__path__") else None
 
         if not os.path.exists(build_ref.so_path()):
             return {"unavailable": "oracle/_ref/gsplat_ref_csrc.so not built (needs /root/reference at build time)"}
