@@ -57,6 +57,10 @@ SIGNATURES = {
     "b200_bin_cull_emit_capacity": (_i, [_i, _i, _p, _p, _p, _u, _u, _u, _u, _f, _f, _p, _p, _sz, _p, _p, _p, _p]),
     "b200_blend_forward_packed_status": (_i, [_u, _u, _u, _u, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "b200_set_record_colors": (_i, [_i, _p, _p, _p]),
+    "b200_densify_accumulate": (_i, [_i, _p, _p, _f, _i, _p, _p, _p, _p]),
+    "b200_densify_ws_bytes": (_sz, [_i, _i]),
+    "b200_densify_plan": (_i, [_i, _p, _p, _p, _p, _p, _f, _f, _f, _f, _i, _f, _f, _f, _i, _p, _sz, _p, _p]),
+    "b200_densify_gather": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_ssim_ws_bytes": (_sz, [_u, _u, _u]),
     "b200_ssim_maps_bytes": (_sz, [_u, _u, _u]),
     "b200_ssim_forward": (_i, [_u, _u, _u, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _p]),

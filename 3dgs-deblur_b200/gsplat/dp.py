@@ -103,6 +103,44 @@ class FlatGaussians:
             new.grad = self.cam_vel.grad
             self.cam_vel = new
 
+    def _reallocate(self, new_n: int):
+        """New flat / gradient buffers for `new_n` Gaussians with the same field order, camera rows and layout rules; the
+        parameter views are rebuilt (contents uninitialised: gsplat.densify.Densifier fills them).  Anything that cached
+        pointers into the old buffers (optimizer, captured graphs) must be rebound by the caller."""
+        K, dev = self.K, self.flat.device
+        n_cam = 0 if self.cam_vel is None else self.cam_vel.shape[0]
+        extra = 6 * n_cam
+        pad = (-(new_n * 11 + extra)) % 4 if self.sh_layout == "block" else 0
+        widths = dict(means=3, log_scales=3, quats=4, opacity_logit=1, sh_dc=3, sh_rest=3 * (K - 1))
+        shapes = dict(means=(new_n, 3), log_scales=(new_n, 3), quats=(new_n, 4), opacity_logit=(new_n, 1), sh_dc=(new_n, 1, 3),
+                      sh_rest=(new_n, K - 1, 3))
+        total = new_n * sum(widths.values()) + extra + pad
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.params, self.slices, self.cam_vel, self.N = {}, {}, None, new_n
+
+        def take(name, off, numel, shape):
+            pr = self.flat[off:off + numel].view(shape).requires_grad_(True)
+            pr.grad = self.flat_grad[off:off + numel].view(shape)
+            self.slices[name] = (off, off + numel)
+            return pr
+
+        off = 0
+        for name in FIELDS:
+            if name == "sh_dc":
+                if extra:
+                    self.cam_vel = take("cam_vel", off, extra, (n_cam, 6))
+                off += extra + pad
+                if self.sh_layout == "block":
+                    self.params["sh"] = take("sh", off, new_n * 3 * K, (new_n, K, 3))
+                    self.slices["sh_dc"] = self.slices["sh_rest"] = self.slices["sh"]
+                    off += new_n * 3 * K
+                    break
+            self.params[name] = take(name, off, new_n * widths[name], shapes[name])
+            off += new_n * widths[name]
+        assert off == total
+        self.sh_start = self.slices["sh_dc"][0]
+
     def sh_coeffs(self) -> torch.Tensor:
         """(N, K, 3) coefficients as spherical_harmonics wants them."""
         if self.sh_layout == "block":
@@ -406,6 +444,7 @@ class PipelinedTrainer:
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.capacity = capacity
         self.vetoed: List[int] = []     # step indices whose update was skipped (the caller repeats those images)
+        self.after_backward = None      # optional callable(absgrad (N,2), radii (N,)) run between phase B and the next phase A
         self.graph_kernel_launches = 0  # libb200splat kernels replayed from captured graphs (the C launch counter only
         #                                 sees launches made through the C ABI, i.e. eager ones and those DURING capture)
         self.steps = 0
@@ -596,6 +635,10 @@ class PipelinedTrainer:
             torch.cuda.current_stream().wait_event(self.ev_sh_done)   # SH parameters of the previous step are final
             self._pending_sh = None
         self._run_B(e, target)
+        if self.after_backward is not None:
+            # e.g. gsplat.densify.Densifier.accumulate: this image's radii and |d loss / d xy| (the `xys.absgrad` side channel)
+            # are both valid exactly here -- phase A of the next image overwrites the projection outputs below
+            self.after_backward(self._geo["xys"].absgrad, self._geo["radii"])
         lo, total = m.sh_start, m.flat.numel()
         works = None
         if self.distributed:
@@ -650,6 +693,23 @@ class PipelinedTrainer:
                 g.mul_(scale)
             self._torch_opts[which].step()
         g.zero_()
+
+    def on_resize(self):
+        """The model's buffers were reallocated (gsplat.densify.Densifier.refine): drop the captured graphs (they address
+        the old buffers), recompute the exchange slices, put the new leaves on this trainer's stream.  The next step
+        re-sizes nothing else: the list capacity follows the polled high-water mark as before."""
+        self.finish()
+        self._graphs.clear()
+        self._geo = None
+        self._prepared = False
+        m = self.model
+        lo, total = m.sh_start, m.flat.numel()
+        n_sh = len(self._sh_bounds)
+        cuts = [lo + ((total - lo) * k // n_sh) // 4 * 4 for k in range(n_sh)] + [total]
+        self._sh_bounds = [(cuts[k], cuts[k + 1]) for k in range(n_sh) if cuts[k + 1] > cuts[k]]
+        if self.cuda:
+            with torch.cuda.stream(self.main):
+                m.rebind_leaves()
 
     def finish(self):
         """Order the caller's stream after everything queued so far, the SH update on the side stream included (call

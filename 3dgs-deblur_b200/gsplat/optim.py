@@ -52,6 +52,15 @@ class FlatAdam:
                                                  self.betas[0], self.betas[1], self.eps, float(grad_scale),
                                                  1 if zero_grad else 0, stream()))
 
+    def rebind(self, flat: torch.Tensor, flat_grad: torch.Tensor):
+        """The parameter buffers were reallocated (densification): fresh zero moments of the new size; the caller fills them
+        (gsplat.densify carries the surviving rows over).  Step count and hyper-parameters stay."""
+        _lib.require_cuda(flat, flat_grad)
+        self.flat, self.flat_grad = flat, flat_grad
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self._ptrs = (flat.data_ptr(), flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr())
+
     def begin_step(self):
         """Once per optimisation step, before the first `update` of that step."""
         self.step_count += 1

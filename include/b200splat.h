@@ -342,6 +342,33 @@ B200_API int b200_blend_forward_packed_status(unsigned img_height, unsigned img_
                                               void *stream);
 B200_API int b200_set_record_colors(int num_points, const float *colors, void *packed, void *stream);
 
+/* ---- adaptive density control on the flat buffers ("next" row f-2 of SURVEY section 8) -----------------------------------
+ * replaces the Python mask / torch.cat / optimizer-state surgery of nerfstudio/models/splatfacto.py:352-622:
+ *   b200_densify_accumulate  after_train (:408-434): grad_norm += |absgrad|, vis_counts += 1, max_2d = max(., radius /
+ *       max(H, W)) for the Gaussians visible in this image (radii > 0); first != 0: the first image since the last
+ *       refinement initialises all three for EVERY Gaussian (norm, 1, 0) like the reference does.
+ *   b200_densify_plan        refinement_after + cull_gaussians (:443-566): every split / duplicate / cull decision and,
+ *       by two prefix sums, the final row of every survivor in the reference's order (kept originals, the children of
+ *       split sample 0, 1, ..., the duplicates).  Negative split_screen_size / cull_scale_thresh / cull_screen_size switch
+ *       that criterion off (the reference's step schedule, :462, :545, :548); do_densify = 0 culls only.
+ *       counts (DEVICE int32[4]): new row count, splits, duplicates, culled originals -- the caller reads it once to size
+ *       the new buffers.  ws: b200_densify_ws_bytes(num_points, n_split_samples) bytes, 256-byte aligned, kept for the gathers.
+ *   b200_densify_gather      writes one field of the new buffers: field 0 copy; 1 means (split children are placed at
+ *       mean + R(q/|q|) (exp(log_scale) * z), z = row sample * n_splits + rank of `randn`, the caller's
+ *       (n_split_samples * n_splits, 3) normal draw, :574-582); 2 log-scales (split children shrink by 1.6, :596);
+ *       3 optimizer moment (children start at zero, :384-399).  src (N, width) -> dst (new count, width). */
+B200_API int b200_densify_accumulate(int num_points, const float *absgrad, const int32_t *radii, float inv_max_dim, int first,
+                                     float *grad_norm, float *vis_counts, float *max_2d, void *stream);
+B200_API size_t b200_densify_ws_bytes(int num_points, int n_split_samples);
+B200_API int b200_densify_plan(int num_points, const float *log_scales, const float *opacity_logit, const float *grad_norm,
+                               const float *vis_counts, const float *max_2d, float half_max_dim, float densify_grad_thresh,
+                               float densify_size_thresh, float split_screen_size, int n_split_samples,
+                               float cull_alpha_thresh, float cull_scale_thresh, float cull_screen_size, int do_densify,
+                               void *ws, size_t ws_bytes, int32_t *counts, void *stream);
+B200_API int b200_densify_gather(int num_points, int n_split_samples, int field, int width, const float *src, float *dst,
+                                 const void *ws, const int32_t *counts, const float *log_scales, const float *quats,
+                                 const float *randn, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
