@@ -51,7 +51,7 @@ static DensifyWs densify_ws(int n, int samps) {
 
 // running statistics of one training image (splatfacto.py:408-434)
 __global__ void __launch_bounds__(256) densify_accumulate_kernel(int n, const float2 *__restrict__ absgrad,
-                                                                 const int32_t *__restrict__ radii, float inv_max_dim,
+                                                                 const int32_t *__restrict__ radii, float max_dim,
                                                                  int first, float *__restrict__ grad_norm,
                                                                  float *__restrict__ vis, float *__restrict__ max2d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) densify_accumulate_kernel(int n, const fl
         vis[i] += 1.f;
         grad_norm[i] += gn;
     }
-    if (visible) max2d[i] = fmaxf(max2d[i], (float)r * inv_max_dim);  // :429-433
+    if (visible) max2d[i] = fmaxf(max2d[i], (float)r / max_dim);  // :429-433 (a true division: r = 40 of 800 must compare equal to 0.05)
 }
 
 // every decision of refinement_after / cull_gaussians for Gaussian i and for its potential children
@@ -180,12 +180,12 @@ __global__ void __launch_bounds__(256) densify_gather_kernel(int n, int samps, i
 
 using namespace b200;
 
-extern "C" int b200_densify_accumulate(int num_points, const float *absgrad, const int32_t *radii, float inv_max_dim, int first,
+extern "C" int b200_densify_accumulate(int num_points, const float *absgrad, const int32_t *radii, float max_dim, int first,
                                        float *grad_norm, float *vis_counts, float *max_2d, void *stream) {
     B200_REQUIRE(num_points >= 1, "num_points must be >= 1");
     B200_REQUIRE(absgrad && radii && grad_norm && vis_counts && max_2d, "null pointer");
     densify_accumulate_kernel<<<ceil_div(num_points, 256), 256, 0, as_stream(stream)>>>(
-        num_points, reinterpret_cast<const float2 *>(absgrad), radii, inv_max_dim, first, grad_norm, vis_counts, max_2d);
+        num_points, reinterpret_cast<const float2 *>(absgrad), radii, max_dim, first, grad_norm, vis_counts, max_2d);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

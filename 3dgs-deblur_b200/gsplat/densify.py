@@ -69,7 +69,7 @@ class Densifier:
         self.last_size = (int(img_height), int(img_width))
         with _lib.on_device(dev):
             check(self.lib.b200_densify_accumulate(n, ptr(absgrad.contiguous().float()), ptr(radii.contiguous()),
-                                                   1.0 / float(max(img_height, img_width)), 1 if first else 0,
+                                                   float(max(img_height, img_width)), 1 if first else 0,
                                                    ptr(self.grad_norm), ptr(self.vis_counts), ptr(self.max_2d), stream()))
 
     def reduce_stats(self, group=None):

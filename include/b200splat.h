@@ -345,7 +345,7 @@ B200_API int b200_set_record_colors(int num_points, const float *colors, void *p
 /* ---- adaptive density control on the flat buffers ("next" row f-2 of SURVEY section 8) -----------------------------------
  * replaces the Python mask / torch.cat / optimizer-state surgery of nerfstudio/models/splatfacto.py:352-622:
  *   b200_densify_accumulate  after_train (:408-434): grad_norm += |absgrad|, vis_counts += 1, max_2d = max(., radius /
- *       max(H, W)) for the Gaussians visible in this image (radii > 0); first != 0: the first image since the last
+ *       max_dim), max_dim = max(H, W), for the Gaussians visible in this image (radii > 0); first != 0: the first image since the last
  *       refinement initialises all three for EVERY Gaussian (norm, 1, 0) like the reference does.
  *   b200_densify_plan        refinement_after + cull_gaussians (:443-566): every split / duplicate / cull decision and,
  *       by two prefix sums, the final row of every survivor in the reference's order (kept originals, the children of
@@ -357,7 +357,7 @@ B200_API int b200_set_record_colors(int num_points, const float *colors, void *p
  *       mean + R(q/|q|) (exp(log_scale) * z), z = row sample * n_splits + rank of `randn`, the caller's
  *       (n_split_samples * n_splits, 3) normal draw, :574-582); 2 log-scales (split children shrink by 1.6, :596);
  *       3 optimizer moment (children start at zero, :384-399).  src (N, width) -> dst (new count, width). */
-B200_API int b200_densify_accumulate(int num_points, const float *absgrad, const int32_t *radii, float inv_max_dim, int first,
+B200_API int b200_densify_accumulate(int num_points, const float *absgrad, const int32_t *radii, float max_dim, int first,
                                      float *grad_norm, float *vis_counts, float *max_2d, void *stream);
 B200_API size_t b200_densify_ws_bytes(int num_points, int n_split_samples);
 B200_API int b200_densify_plan(int num_points, const float *log_scales, const float *opacity_logit, const float *grad_norm,

@@ -41,7 +41,7 @@ def test_densifier_matches_the_oracle(layout, step):
             dens.accumulate(absgrad.cuda(), radii.cuda(), H, W, step)
             DO.accumulate(stats, absgrad, radii, H, W)
         for k, t in (("grad_norm", dens.grad_norm), ("vis_counts", dens.vis_counts), ("max_2d", dens.max_2d)):
-            torch.testing.assert_close(t.cpu(), stats[k], rtol=1e-6, atol=1e-9)
+            torch.testing.assert_close(t.cpu(), stats[k], rtol=1e-6 if k == "grad_norm" else 0, atol=1e-9 if k == "grad_norm" else 0)
     else:
         dens.last_size = (H, W)
     names = [k for k in model.params]
