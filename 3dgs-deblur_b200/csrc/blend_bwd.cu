@@ -279,8 +279,11 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
 //   * sigma, exp, alpha for both pixels in straight-line code; pixels that fail a test are masked by zeroing `vis` and
 //     `alpha` (then fac, v_sigma and every accumulated term are exactly 0 and T is kept by a select) -- one vote decides
 //     whether the gradient algebra runs at all.
+#ifndef B200_BWD_MIN_CTAS
+#define B200_BWD_MIN_CTAS 5  // 96 registers; A/B of 4 / 6 in DESIGN.md section 9
+#endif
 template <int S>
-__global__ void __launch_bounds__(128, 5) blend_backward_kernel2(const BlendBwdParams p) {
+__global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2(const BlendBwdParams p) {
     constexpr int NT = 128;
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];

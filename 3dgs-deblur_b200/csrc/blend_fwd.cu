@@ -223,8 +223,11 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 6 : 1) blend_f
 // three colour accumulations issue once for both pixels (FFMA2 / FMUL2 / FADD2), failed tests mask instead of branching
 // (alpha = 0 leaves T, the colour sums and `last` untouched), and one warp vote per sample skips the blend arithmetic
 // when no lane passes.  The branchy one-pixel-at-a-time form costs ~32 issue slots per pixel-sample, this ~23.
+#ifndef B200_FWD_MIN_CTAS
+#define B200_FWD_MIN_CTAS 6  // 80 registers
+#endif
 template <int S>
-__global__ void __launch_bounds__(128, 6) blend_forward_kernel2(const BlendFwdParams p) {
+__global__ void __launch_bounds__(128, B200_FWD_MIN_CTAS) blend_forward_kernel2(const BlendFwdParams p) {
     constexpr int NT = 128;
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
