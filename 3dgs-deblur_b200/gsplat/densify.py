@@ -150,7 +150,7 @@ class Densifier:
             fields = [k for k in old if k in m.params]
             for name in fields:
                 width = old[name][0].numel()
-                field = {"means": 1, "log_scales": 2}.get(name, 0)
+                field = {"means": 1 if z is not None else 0, "log_scales": 2}.get(name, 0)  # (no split, no re-sampled child)
                 check(lib.b200_densify_gather(n, samps, field, width, ptr(old[name]), ptr(m.params[name]), ptr(ws), ptr(counts),
                                               ptr(old["log_scales"]), ptr(old["quats"]), ptr(z), stream()))
                 if self.adam is not None:
