@@ -17,6 +17,7 @@ The densification statistics (xys.absgrad norms, visibility counts, max 2D radiu
 splatfacto.py:417-434) are exposed by `reduce_densify_stats` with the matching sum / sum / max
 reductions so a caller can keep topology changes identical across ranks.
 """
+import math
 from typing import Dict, List, Optional
 
 import torch
@@ -390,6 +391,24 @@ def shading_phase(model: FlatGaussians, geo: Dict, scene: Dict, target: torch.Te
     loss = loss_fn(rgb, target)
     loss.backward()
     return loss.detach()
+
+
+def balanced_assignment(costs, world: int):
+    """Cost-aware batching for synchronous data parallelism.  A step lasts as long as its slowest rank, and images differ
+    in cost (tile-list length: +-20 % at BASELINE config 2), so a random group of `world` images wastes the difference to
+    the group's maximum on every other rank.  costs: one number per image (e.g. the list entries phase A reports in
+    status[1]); returns steps[j][r] = index of the image rank r renders in step j, every image used exactly once per
+    pass, each step made of images adjacent in the cost order (length-bucketing, as sequence models do).  The step ORDER
+    is then shuffled deterministically so consecutive steps do not walk the cost ramp."""
+    n = len(costs)
+    if n % world:
+        raise ValueError("balanced_assignment: the number of images must be a multiple of the world size")
+    order = sorted(range(n), key=lambda i: (-float(costs[i]), i))
+    steps = [order[j * world:(j + 1) * world] for j in range(n // world)]
+    # a fixed permutation of the steps: stride through them with a step count coprime to their number
+    m = len(steps)
+    stride = next((s_ for s_ in range(max(2, m // 2) | 1, 2 * m + 3, 2) if math.gcd(s_, m) == 1), 1) if m > 2 else 1
+    return [steps[(k * stride) % m] for k in range(m)]
 
 
 class PipelinedTrainer:

@@ -23,7 +23,7 @@ def _workspace(dev):
 
 class _L1Loss(Function):
     @staticmethod
-    def forward(ctx, pred, target):
+    def forward(ctx, pred, target, gamma=None):
         _lib.require_cuda(pred, target)
         if pred.shape != target.shape:
             raise ValueError(f"l1_loss: shapes differ: {tuple(pred.shape)} vs {tuple(target.shape)}")
@@ -36,8 +36,14 @@ class _L1Loss(Function):
         with _lib.on_device(dev):
             loss = torch.empty((), dtype=torch.float32, device=dev)
             grad = torch.empty_like(pred_c) if ctx.needs_input_grad[0] else None
-            check(_lib.load().b200_l1_loss(pred_c.numel(), ptr(pred_c), ptr(target_c), ptr(loss), ptr(grad),
-                                           ptr(_workspace(dev)), 1, stream()))
+            if gamma is None:
+                check(_lib.load().b200_l1_loss(pred_c.numel(), ptr(pred_c), ptr(target_c), ptr(loss), ptr(grad),
+                                               ptr(_workspace(dev)), 1, stream()))
+            else:  # pred is the LINEAR render: gamma correction and its backward ride in the same kernel
+                if not float(gamma) > 0.0:
+                    raise ValueError("l1_loss: gamma must be positive")
+                check(_lib.load().b200_l1_loss_gamma(pred_c.numel(), ptr(pred_c), ptr(target_c), float(gamma), ptr(loss), ptr(grad),
+                                                     ptr(_workspace(dev)), 1, stream()))
         ctx.grad = grad
         ctx.target_needs = ctx.needs_input_grad[1]
         return loss
@@ -48,12 +54,16 @@ class _L1Loss(Function):
             raise RuntimeError("l1_loss: the target image is a constant (no gradient)")
         g = ctx.grad
         ctx.grad = None
-        return (g * v_loss if g is not None else None), None
+        return (g * v_loss if g is not None else None), None, None
 
 
-def l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-    """mean |pred - target| as a 0-d tensor; differentiable w.r.t. `pred` only."""
-    return _L1Loss.apply(pred, target)
+def l1_loss(pred: torch.Tensor, target: torch.Tensor, gamma: float = None) -> torch.Tensor:
+    """mean |pred - target| as a 0-d tensor; differentiable w.r.t. `pred` only.
+
+    gamma (extension): `pred` is the LINEAR render and the loss is taken on the caller's gamma-corrected image,
+    mean |clamp(pred, max=1) ** (1 / gamma) - target| (splatfacto.py:879-880 followed by :957) -- correction, loss and the
+    cotangent w.r.t. the linear image in one kernel instead of clamp / pow forward and their three backward passes."""
+    return _L1Loss.apply(pred, target, gamma)
 
 
 # ---- SSIM and the full photometric loss (splatfacto.py:957-975) -------------------------------------------------

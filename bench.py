@@ -84,6 +84,9 @@ def parse():
                          "2-5); scene = whole scenes shard across the GPUs (BASELINE config 5: `--config c5 --mode scene`): rank r "
                          "trains scene r mod --scenes, ranks that share a scene form an image-sharded group, no exchange between scenes")
     ap.add_argument("--scenes", type=int, default=5, help="number of independent scenes in --mode scene")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: keep the default image -> (step, rank) assignment instead of grouping images of similar cost "
+                         "(gsplat.dp.balanced_assignment) so that no rank waits for a much slower one")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-kernel measurements (ref_gpu key)")
     ap.add_argument("--trainer", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined = gsplat.dp.PipelinedTrainer (no host sync, CUDA graphs, exchange behind the next image's "
@@ -407,6 +410,38 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- cost-aware batching (N > 1): a synchronous step lasts as long as its slowest rank, and images differ in cost (tile
+    # list entries 0.6-0.84 M at config 2).  One pass measures every image's entries (phase A's status word), the ranks
+    # share them, and gsplat.dp.balanced_assignment regroups the SAME images so that each step holds images of similar cost.
+    balance = None
+    if world > 1 and pipelined and args.mode == "image" and not args.no_balance:
+        from gsplat.dp import balanced_assignment
+
+        local = [0] * n_img
+        for i in range(n_img + 1):
+            stepper.step(i)
+            trainer.finish()
+            torch.cuda.synchronize()
+            local[(i + 1) % n_img] = int(trainer.status[1])  # (step i also prepared image i + 1: its entries are in the status word)
+        gathered = [torch.zeros(n_img, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor(local, dtype=torch.int64, device=dev))
+        costs = [0] * (n_img * world)
+        for r_ in range(world):
+            for i in range(n_img):
+                costs[i * world + r_] = int(gathered[r_][i])
+        steps_ = balanced_assignment(costs, world)
+        mine = [steps_[j][rank] for j in range(n_img)]
+        spread = lambda groups: sum(max(costs[g] for g in grp) / (sum(costs[g] for g in grp) / world) for grp in groups) / len(groups)
+        balance = {"max_over_mean_cost_before": round(spread([[i * world + r_ for r_ in range(world)] for i in range(n_img)]), 4),
+                   "max_over_mean_cost_after": round(spread(steps_), 4), "cost": "tile-list entries after culling (phase A status word)"}
+        my[:] = [scene["cameras"][g] for g in mine]
+        new_cams = make_cameras(dict(scene_dev, cameras=my), dev, not args.no_vel_grad)
+        cams[:] = new_cams
+        targets_u8[:] = [(c["target"] * 255).to(torch.uint8).contiguous().pin_memory() for c in my]
+        targets[:] = [t.to(dev).float() / 255 for t in targets_u8]
+        cam_rows[:] = [torch.cat([c["viewmat"].reshape(-1), c["lin_vel"], c["ang_vel"], c["cam_pos"]]).contiguous() for c in cams]
+        stepper.staged = None
+
     # ---- kernel-resident metric: inputs already in HBM, CUDA-event timing, max over ranks
     # warm-up: at least one pass over every training image, so no timed step meets a new camera (first-use allocations,
     # list capacities) -- args.warmup is a lower bound
@@ -705,7 +740,7 @@ def run_gpu_arm(args):
                     "trainer": ("gsplat.dp.PipelinedTrainer: no host sync (capacity-mode tile lists, device-side veto), two CUDA "
                                 "graphs per step, gradient exchange + SH update behind the next image's projection/binning"
                                 if pipelined else "gsplat.dp.ImageShardedTrainer (one host sync per step, eager launches)"),
-                    "trainer_status": trainer_status},
+                    "trainer_status": trainer_status, "balance": balance},
         "step_ms": step_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }

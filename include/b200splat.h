@@ -269,6 +269,11 @@ B200_API int b200_nd_rasterize_backward(int num_points, unsigned img_height, uns
 B200_API size_t b200_l1_loss_ws_bytes(void);
 B200_API int b200_l1_loss(long long numel, const float *pred, const float *target, float *loss, float *grad, void *ws,
                           int ws_is_zeroed, void *stream);
+/* The same with the caller's gamma step folded in (splatfacto.py:879-880 `clamp(rgb, max=1) ** (1 / gamma)` before the loss of
+ * :957): pred_linear is the LINEAR render, loss[0] = mean |min(pred, 1)^(1/gamma) - target|, grad_linear = the cotangent w.r.t.
+ * the linear image (torch's clamp / pow backward: (1/gamma) x^(1/gamma - 1) up to and including x = 1, 0 above, infinite at 0). */
+B200_API int b200_l1_loss_gamma(long long numel, const float *pred_linear, const float *target, float gamma, float *loss,
+                                float *grad_linear, void *ws, int ws_is_zeroed, void *stream);
 
 /* SSIM term of the photometric loss, (1 - lambda) * L1 + lambda * (1 - SSIM) (nerfstudio/models/splatfacto.py:957-975;
  * SSIM = pytorch_msssim.SSIM(data_range=1, size_average=True, channel=C): 11-tap Gaussian window sigma 1.5, separable,

@@ -67,3 +67,25 @@ def test_ssim_identities_and_errors():
         ssim(p, t)  # CPU tensors: no CPU path
     with pytest.raises(RuntimeError):
         photometric_loss(pc.double(), tc.double())
+
+
+def test_l1_loss_with_the_gamma_step_folded_in():
+    """l1_loss(linear, target, gamma) == mean |clamp(linear, max=1) ** (1 / gamma) - target| (splatfacto.py:879-880 then :957)
+    and its autograd cotangent w.r.t. the LINEAR image, incl. the zero slope above the clamp."""
+    from gsplat.losses import l1_loss
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape in ((800, 800, 3), (37, 53, 3)):
+        lin = (torch.rand(shape, device="cuda", generator=g) * 1.4 + 0.01).requires_grad_(True)  # some pixels above 1
+        with torch.no_grad():
+            lin.view(-1)[1] = 1.0  # exactly at the clamp: the gradient still flows (torch's clamp backward is inclusive)
+        target = torch.rand(shape, device="cuda", generator=g)
+        ref = (torch.clamp(lin, max=1.0) ** (1.0 / 2.2) - target).abs().mean()
+        (g_ref,) = torch.autograd.grad(ref * 2.0, lin)
+        out = l1_loss(lin, target, gamma=2.2)
+        (g_out,) = torch.autograd.grad(out * 2.0, lin)
+        torch.testing.assert_close(out, ref, rtol=3e-6, atol=0)
+        torch.testing.assert_close(g_out, g_ref, rtol=2e-5, atol=1e-12)
+        assert float(g_out[lin.detach() > 1.0].abs().max()) == 0.0 and float(g_out.view(-1)[1].abs()) > 0.0
+    with pytest.raises(ValueError):
+        l1_loss(lin, target, gamma=0.0)
