@@ -46,9 +46,12 @@ def _oracle_backward_chain(d, r, v_out, v_alpha):
     return rb, v_sh, pb, v_opac, v_bg
 
 
-def _check_forward(img, alpha, r, what, outliers=1e-3):
-    close(img, r["img"], 5e-5, 1e-4, what + " image", outliers=outliers, outlier_atol=1e-2)
-    close(alpha, 1 - r["final_Ts"].mean(-1), 5e-5, 1e-4, what + " alpha", outliers=outliers, outlier_atol=1e-2)
+def _check_forward(img, alpha, r, what, conditioned=False):
+    """conditioned: the scene holds near-plane splats whose fp32 projection differs by 1-2 px between fused and unfused
+    multiply-adds (see test_full_size_operator_chain_vs_oracle): 1e-3 absolute instead of 5e-5."""
+    atol = 1e-3 if conditioned else 5e-5
+    close(img, r["img"], atol, 1e-4, what + " image", outliers=1e-3, outlier_atol=1e-2)
+    close(alpha, 1 - r["final_Ts"].mean(-1), atol, 1e-4, what + " alpha", outliers=1e-3, outlier_atol=1e-2)
     mse = float(((img.detach().cpu().numpy().astype(np.float64) - r["img"]) ** 2).mean())
     assert mse < 1e-8, f"{what}: PSNR {10 * np.log10(1.0 / max(mse, 1e-30)):.1f} dB vs the oracle (bar: 80 dB)"
 
@@ -182,9 +185,10 @@ def test_fused_render_vs_oracle_chain(name, n, H, W, S, rs, ex):
         lv["means"], lv["log_scales"], lv["quats"], lv["opacity_logit"], lv["sh_dc"], lv["sh_rest"], cu(d["viewmat"]),
         cu(d["cam_pos"]), lin, ang, d["fx"], d["fy"], d["cx"], d["cy"], d["H"], d["W"], 16, bg,
         rolling_shutter_time=d["rs"], exposure_time=d["exposure"], blur_samples=d["S"], sh_degree_to_use=3)
-    # the fused kernel's sigmoid (ex2-based) and SH dot product round differently from torch's: a last-bit change of an
-    # opacity flips an `alpha >= 1/255` test here and there -- 1.5e-3 of the pixels of the small rolling-shutter case
-    _check_forward(img, alpha, r, f"{name} fused", outliers=1e-3 if n is None else 3e-3)
+    # the 40k-Gaussian rolling-shutter case keeps 173 splats within z < 0.1 of the camera plane: projection conditioning as in
+    # test_full_size_operator_chain_vs_oracle (tools/scratch/diag_fused.py on the B200: fused and operator chain both differ
+    # from the oracle in 2.5 % of the alpha pixels by <= 1.3e-3, the same kernels on the ORACLE's projection in 1e-5 of them)
+    _check_forward(img, alpha, r, f"{name} fused", conditioned=n is not None)
     g = np.random.default_rng(6)
     v_out = g.standard_normal(r["img"].shape).astype(np.float32)
     v_alpha = g.standard_normal(r["img"].shape[:2]).astype(np.float32)
