@@ -702,6 +702,14 @@ def run_gpu_arm(args):
                                  "peak": peak_li, "unit": "lane-instr/s", "frac": round(ach / peak_li, 4),
                                  "peak_source": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock sampled during the timed region)" % (
                                      sms, clocks["sm_mhz"])}
+                        if tj[dom].get("pixel_sample_evaluations"):
+                            # what the issued instructions buy: (pixel, sample, Gaussian) evaluations executed per launch and
+                            # the share of them that passes the reference's sigma / alpha tests (the -DB200_BLEND_COUNTERS build)
+                            ev, ok_ = tj[dom]["pixel_sample_evaluations"], tj[dom]["evaluations_passing_the_alpha_test"]
+                            issue.update(evaluations_per_launch=ev, useful_evaluations_per_launch=ok_,
+                                         useful_fraction=round(ok_ / ev, 4),
+                                         useful_evaluations_per_s=ok_ / (kernels[dom]["ms"] * 1e-3),
+                                         note=tj[dom].get("packed_fp32x2_note"))
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                         "frac": round(kernels[dom]["gbs"] / peak, 5), "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": peak_src, "issue": issue,
