@@ -87,6 +87,7 @@ def parse():
     ap.add_argument("--no-balance", action="store_true",
                     help="N > 1: keep the default image -> (step, rank) assignment instead of grouping images of similar cost "
                          "(gsplat.dp.balanced_assignment) so that no rank waits for a much slower one")
+    ap.add_argument("--timeline", default=None, help="rank 0: write a CUPTI kernel timeline (start, duration, stream, name) of 6 steps to this file")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-kernel measurements (ref_gpu key)")
     ap.add_argument("--trainer", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined = gsplat.dp.PipelinedTrainer (no host sync, CUDA graphs, exchange behind the next image's "
@@ -501,6 +502,27 @@ def run_gpu_arm(args):
         fused_path = {"value": world * 1000.0 / float(tf.item()), "unit": "images/s", "ms_per_step": float(tf.item()),
                       "steps": fsteps, "api": "gsplat.fused.render_gaussians (raw parameters in, one operator; caller-modified)"}
         del trainer_f, model_f
+
+    if args.timeline:  # every rank steps (collectives), rank 0 records
+        from torch.profiler import ProfilerActivity, profile
+
+        k0 = stepper.staged if (pipelined and stepper.staged is not None) else 0
+        if rank == 0:
+            with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
+                for k in range(6):
+                    stepper.step(k0 + k)
+                torch.cuda.synchronize()
+            from torch.autograd import DeviceType
+            evs = sorted((e for e in prof_t.events() if e.device_type == DeviceType.CUDA), key=lambda e: e.time_range.start)
+            t0_ = evs[0].time_range.start if evs else 0
+            with open(args.timeline, "w") as f:
+                f.write("start_us\tdur_us\tname\n")
+                for e in evs:
+                    f.write(f"{e.time_range.start - t0_:.1f}\t{e.time_range.end - e.time_range.start:.1f}\t{e.name[:90]}\n")
+        else:
+            for k in range(6):
+                stepper.step(k0 + k)
+            torch.cuda.synchronize()
 
     gpu_busy = None
     if args.profile and rank == 0:
