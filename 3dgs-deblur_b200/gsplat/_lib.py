@@ -45,6 +45,8 @@ SIGNATURES = {
                                         _p, _p, _p, _p, _p, _p, _i, _p]),
     "b200_fused_preprocess_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _u, _u, _u,
                                            _f, _p, _p, _p, _p, _p]),
+    "b200_fused_geometry_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _u, _u, _u, _f, _p, _p, _p, _p, _p]),
+    "b200_fused_colors_forward": (_i, [_i, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "b200_fused_preprocess_backward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _u, _u,
                                             _u, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

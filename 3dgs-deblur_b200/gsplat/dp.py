@@ -45,9 +45,9 @@ class FlatGaussians:
         shapes = dict(means=(N, 3), log_scales=(N, 3), quats=(N, 4), opacity_logit=(N, 1), sh_dc=(N, 1, 3),
                       sh_rest=(N, K - 1, 3))
         extra = 6 * n_cameras if optimize_velocities else 0
-        # "block": pad the camera rows so the SH block starts on a 16-byte boundary (the slice-wise device-state Adam and
+        # pad the camera rows so the SH coefficients start on a 16-byte boundary (the slice-wise device-state Adam and
         # the SH kernels' vector accesses want that)
-        pad = (-(N * 11 + extra)) % 4 if sh_layout == "block" else 0
+        pad = (-(N * 11 + extra)) % 4
         total = N * sum(widths.values()) + extra + pad
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.flat_grad = torch.zeros_like(self.flat)
@@ -111,7 +111,7 @@ class FlatGaussians:
         K, dev = self.K, self.flat.device
         n_cam = 0 if self.cam_vel is None else self.cam_vel.shape[0]
         extra = 6 * n_cam
-        pad = (-(new_n * 11 + extra)) % 4 if self.sh_layout == "block" else 0
+        pad = (-(new_n * 11 + extra)) % 4
         widths = dict(means=3, log_scales=3, quats=4, opacity_logit=1, sh_dc=3, sh_rest=3 * (K - 1))
         shapes = dict(means=(new_n, 3), log_scales=(new_n, 3), quats=(new_n, 4), opacity_logit=(new_n, 1), sh_dc=(new_n, 1, 3),
                       sh_rest=(new_n, K - 1, 3))
@@ -393,6 +393,91 @@ def shading_phase(model: FlatGaussians, geo: Dict, scene: Dict, target: torch.Te
     return loss.detach()
 
 
+def fused_geometry_phase(model: FlatGaussians, st: Dict, scene: Dict, capacity: int, status: torch.Tensor):
+    """Phase A straight on the C ABI, raw parameters in: ONE kernel (b200_fused_geometry_forward: exp, quaternion
+    normalisation, projection, sigmoid * compensation, blend record -- what `geometry_phase` spends 11 launches on, 8 of
+    them PyTorch glue) + the capacity-mode binning.  Same interface and the same numbers as `geometry_phase` up to
+    float rounding of the activations.  No autograd graph: `fused_shading_phase` differentiates with
+    b200_fused_preprocess_backward."""
+    import gsplat.cuda as _C
+    from gsplat import _lib
+    from gsplat._lib import check, ptr, stream
+
+    p = model.params
+    cam = st["cam"]
+    with torch.no_grad():
+        if model.cam_vel is not None:  # per-camera velocity rows (disjoint across images): row cam_index + dataset value
+            vel = model.cam_vel.detach().index_select(0, st["cam_index"])[0] + cam[12:18]
+        else:
+            vel = cam[12:18]
+        H, W, bw = scene["H"], scene["W"], scene["block_width"]
+        rs, ex = float(scene["rolling_shutter_time"]), float(scene["exposure_time"])
+        blur = scene["blur_samples"] if ex > 0 else 1
+        n, dev = model.N, model.flat.device
+        lib = _lib.load()
+        with _lib.on_device(dev):
+            packed = torch.empty((n * lib.b200_packed_record_bytes(),), dtype=torch.uint8, device=dev)
+            depths = torch.empty((n,), dtype=torch.float32, device=dev)
+            radii = torch.empty((n,), dtype=torch.int32, device=dev)
+            nth = torch.empty((n,), dtype=torch.int32, device=dev)
+            check(lib.b200_fused_geometry_forward(
+                n, ptr(p["means"]), ptr(p["log_scales"]), ptr(p["quats"]), ptr(p["opacity_logit"]), ptr(cam), ptr(vel[:3]),
+                ptr(vel[3:]), rs, ex, float(scene["fx"]), float(scene["fy"]), float(scene["cx"]), float(scene["cy"]), H, W, bw,
+                _CLIP_THRESH, ptr(packed), ptr(depths), ptr(radii), ptr(nth), stream()))
+            ids, bins = _C.bin_cull_capacity(packed, depths, radii, nth, H, W, bw, blur, rs, ex, capacity, status)
+    return dict(packed=packed, depths=depths, radii=radii, num_tiles_hit=nth, ids=ids, bins=bins, vel=vel, cam=cam,
+                cam_index=st["cam_index"], status=status, blur=blur, absgrad=None)
+
+
+def fused_shading_phase(model: FlatGaussians, geo: Dict, scene: Dict, target: torch.Tensor, loss_fn, sh_degree_to_use: int = 3):
+    """Phase B on the C ABI: SH colours into the records (b200_fused_colors_forward), blend, `loss_fn` (autograd sees
+    only loss_fn(rgb, target)), blend backward, and ONE kernel for everything behind it (b200_fused_preprocess_backward:
+    SH, clamp, sigmoid * compensation, projection VJP, exp, normalisation) that writes the model's flat gradient buffer
+    row by row -- no accumulate passes, no memsets.  The gradient rows are OVERWRITTEN (the buffer is zero between steps:
+    FlatAdam clears what it consumes); the camera-velocity row is accumulated."""
+    import gsplat.cuda as _C
+    from gsplat import _lib
+    from gsplat._lib import check, ptr, stream
+
+    if model.sh_layout != "split":
+        raise ValueError("fused_shading_phase reads sh_dc / sh_rest apart: build the model with sh_layout='split'")
+    p = model.params
+    H, W, bw = scene["H"], scene["W"], scene["block_width"]
+    rs, ex = float(scene["rolling_shutter_time"]), float(scene["exposure_time"])
+    fx, fy, cx, cy = (float(scene[k]) for k in ("fx", "fy", "cx", "cy"))
+    n, K, S, dev = model.N, model.K, geo["blur"], model.flat.device
+    cam, vel, packed, radii = geo["cam"], geo["vel"], geo["packed"], geo["radii"]
+    cam_pos = cam[18:21]
+    bg = scene["background"]
+    lib = _lib.load()
+    with torch.no_grad(), _lib.on_device(dev):
+        check(lib.b200_fused_colors_forward(n, ptr(p["means"]), ptr(p["sh_dc"]), ptr(p["sh_rest"]), K, sh_degree_to_use,
+                                            ptr(cam_pos), ptr(radii), ptr(packed), stream()))
+        rgb, Ts, fi = _C.blend_forward_packed(H, W, bw, S, geo["ids"], geo["bins"], packed, rs, ex, bg, status=geo["status"])
+    rgb.requires_grad_(True)
+    with torch.enable_grad():
+        loss = loss_fn(rgb, target)
+    (v_rgb,) = torch.autograd.grad(loss, rgb)
+    with torch.no_grad(), _lib.on_device(dev):
+        v_xy, v_abs, v_pix, v_conic, v_col, v_op = _C.blend_backward_packed(
+            n, H, W, bw, S, geo["ids"], geo["bins"], packed, rs, ex, bg, Ts, fi, v_rgb, None)
+        g = {name: model.flat_grad[a:b_] for name, (a, b_) in model.slices.items()}
+        g_vel = torch.empty(6, dtype=torch.float32, device=dev) if model.cam_vel is not None else None
+        check(lib.b200_fused_preprocess_backward(
+            n, ptr(p["means"]), ptr(p["log_scales"]), ptr(p["quats"]), ptr(p["opacity_logit"]), ptr(p["sh_dc"]),
+            ptr(p["sh_rest"]), K, sh_degree_to_use, ptr(cam), ptr(cam_pos), ptr(vel[:3]), ptr(vel[3:]), rs, ex, fx, fy, cx, cy,
+            H, W, bw, _CLIP_THRESH, ptr(packed), ptr(radii), ptr(v_xy), ptr(v_pix), ptr(v_conic), ptr(v_col), ptr(v_op),
+            ptr(g["means"]), ptr(g["log_scales"]), ptr(g["quats"]), ptr(g["opacity_logit"]), ptr(g["sh_dc"]), ptr(g["sh_rest"]),
+            ptr(g_vel[:3]) if g_vel is not None else None, ptr(g_vel[3:]) if g_vel is not None else None, None, stream()))
+        if g_vel is not None:
+            g["cam_vel"].view(-1, 6).index_add_(0, geo["cam_index"], g_vel.view(1, 6))
+    geo["absgrad"] = v_abs   # the `xys.absgrad` side channel of the drop-in operator (densification statistic)
+    return loss.detach()
+
+
+_CLIP_THRESH = 0.01  # project_gaussians' default near plane (gsplat/gsplat/project_gaussians.py:31)
+
+
 def balanced_assignment(costs, world: int):
     """Cost-aware batching for synchronous data parallelism.  A step lasts as long as its slowest rank, and images differ
     in cost (tile-list length: +-20 % at BASELINE config 2), so a random group of `world` images wastes the difference to
@@ -438,14 +523,26 @@ class PipelinedTrainer:
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, loss_fn=None, use_graphs: bool = True,
                  capacity: Optional[int] = None, sh_degree_to_use: int = 3, geometry_fn=None, shading_fn=None,
-                 optimizer: str = "b200", sh_chunks: int = 2):
+                 optimizer: str = "b200", sh_chunks: int = 2, operators: Optional[str] = None):
+        """operators: "dropin" = the two phases on the reference-compatible operators under autograd (`geometry_phase` /
+        `shading_phase`); "fused" = on the fused raw-parameter kernels (`fused_geometry_phase` / `fused_shading_phase`:
+        same numbers, ~45 fewer launches per step); None = fused where it applies (CUDA, sh_layout "split"), else drop-in."""
         self.model, self.scene = model, dict(scene)
         if loss_fn is None:
             from gsplat.losses import l1_loss as loss_fn
         self.loss_fn = loss_fn
         self.sh_degree = sh_degree_to_use
-        self.geometry_fn = geometry_fn or geometry_phase   # (tests inject CPU stand-ins with the same interface)
-        self.shading_fn = shading_fn or shading_phase
+        fusable = model.flat.device.type == "cuda" and model.sh_layout == "split"
+        if operators is None:
+            operators = "fused" if fusable else "dropin"
+        if operators not in ("fused", "dropin"):
+            raise ValueError("operators must be 'fused', 'dropin' or None")
+        if operators == "fused" and not fusable and geometry_fn is None:
+            raise ValueError("operators='fused' needs a CUDA model with sh_layout='split'")
+        self.operators = operators
+        phases = (fused_geometry_phase, fused_shading_phase) if operators == "fused" else (geometry_phase, shading_phase)
+        self.geometry_fn = geometry_fn or phases[0]   # (tests inject CPU stand-ins with the same interface)
+        self.shading_fn = shading_fn or phases[1]
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.group = group
         self.rank = dist.get_rank(group) if self.distributed else 0
@@ -498,7 +595,7 @@ class PipelinedTrainer:
             self.main = torch.cuda.Stream(device=dev)
             self.side = torch.cuda.Stream(device=dev)
             model.rebind_leaves()  # gradient accumulators are (re)created on `main` by the first step
-            self.ev_prepared, self.ev_sh_done = torch.cuda.Event(), torch.cuda.Event()
+            self.ev_prepared, self.ev_sh_done, self.ev_poll = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
             self._host_words = torch.zeros(2, 24, dtype=torch.int32).pin_memory()   # status (4) | adam state (16) | quat flag
             self._host_ev = [torch.cuda.Event(), torch.cuda.Event()]
             self._host_seen = [False, False]
@@ -657,7 +754,8 @@ class PipelinedTrainer:
         if self.after_backward is not None:
             # e.g. gsplat.densify.Densifier.accumulate: this image's radii and |d loss / d xy| (the `xys.absgrad` side channel)
             # are both valid exactly here -- phase A of the next image overwrites the projection outputs below
-            self.after_backward(self._geo["xys"].absgrad, self._geo["radii"])
+            absgrad = self._geo["absgrad"] if "absgrad" in self._geo else self._geo["xys"].absgrad
+            self.after_backward(absgrad, self._geo["radii"])
         lo, total = m.sh_start, m.flat.numel()
         works = None
         if self.distributed:
@@ -675,14 +773,15 @@ class PipelinedTrainer:
             self.flag.zero_()
             if veto_host:
                 self.vetoed.append(self.steps)
+        # the next image's camera row is staged while the geometry gradients are on the wire (B, its last reader, is queued)
+        self._prepared = False
+        if next_cam is not None:
+            self._prepare(next_cam, next_index)
         if works is not None:
             works[0].wait()
         self._update(0, lo, scale, veto_host, 0)
         self._poll_host()
         # ---- next image's geometry (needs only the rows just updated), SH update beside it
-        self._prepared = False
-        if next_cam is not None:
-            self._prepare(next_cam, next_index)
         if self.cuda:
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_prepared)
@@ -748,13 +847,19 @@ class PipelinedTrainer:
             self._consume(self._host_words[other])
             self._host_seen[other] = False
         w = self._host_words[slot]
-        w[0:4].copy_(self.status, non_blocking=True)
-        w[4:20].copy_(self.adam.state, non_blocking=True)
-        from gsplat import _lib
-        qf = _lib._quat_flags.get(self.device.index)
-        if qf is not None:
-            w[20:21].copy_(qf, non_blocking=True)
-        self._host_ev[slot].record()
+        # the three small transfers go on the side stream (idle here: the previous SH update finished before phase B), so
+        # the next image's geometry does not queue behind them; the words may then mix this step's counters with the next
+        # image's (phase A runs beside the copies) -- every consumer below is monotone (running max, veto count + ring)
+        self.ev_poll.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_poll)
+            w[0:4].copy_(self.status, non_blocking=True)
+            w[4:20].copy_(self.adam.state, non_blocking=True)
+            from gsplat import _lib
+            qf = _lib._quat_flags.get(self.device.index)
+            if qf is not None:
+                w[20:21].copy_(qf, non_blocking=True)
+            self._host_ev[slot].record(self.side)
         self._host_seen[slot] = True
 
     def _consume(self, w):

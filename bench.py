@@ -62,6 +62,18 @@ def usable_cores():
     return max(1, n)
 
 
+def _layout(operators):
+    """FlatGaussians SH layout each operator set reads: fused kernels take sh_dc / sh_rest apart, spherical_harmonics one block."""
+    return "split" if operators == "fused" else "block"
+
+
+def _api(operators):
+    if operators == "fused":
+        return ("C ABI raw-parameter kernels: b200_fused_geometry_forward + b200_bin_cull_* | b200_fused_colors_forward + "
+                "b200_blend_*_packed + b200_fused_preprocess_backward (gsplat.dp.fused_geometry_phase / fused_shading_phase)")
+    return "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians under autograd"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -92,6 +104,10 @@ def parse():
     ap.add_argument("--trainer", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined = gsplat.dp.PipelinedTrainer (no host sync, CUDA graphs, exchange behind the next image's "
                          "geometry); sync = gsplat.dp.ImageShardedTrainer (round-1 path: one host sync per step, eager)")
+    ap.add_argument("--operators", default="fused", choices=["fused", "dropin"],
+                    help="pipelined trainer phases: fused = the raw-parameter kernels on the C ABI (b200_fused_geometry_forward / "
+                         "_colors_forward / _preprocess_backward, no autograd glue); dropin = gsplat.project_gaussians / "
+                         "spherical_harmonics / rasterize_gaussians under autograd")
     ap.add_argument("--no-graphs", action="store_true", help="pipelined trainer without CUDA-graph capture (debug / A-B)")
     ap.add_argument("--fused", action="store_true",
                     help="render through gsplat.fused.render_gaussians (caller-modified 'next' path) instead of the drop-in operators")
@@ -307,8 +323,8 @@ def measure_ref_gpu(args, scene_dev, cams, targets, n_img, value, loss_fn, dev):
         for c in cams:
             z = torch.zeros(3, device=dev)
             rows0.append(torch.cat([c["viewmat"].reshape(-1), z, z, c["cam_pos"]]).contiguous())
-        m0 = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=True, sh_layout="block")
-        t0 = PipelinedTrainer(m0, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs)
+        m0 = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=True, sh_layout=_layout(args.operators))
+        t0 = PipelinedTrainer(m0, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs, operators=args.operators)
         t0.prepare(rows0[0], 0)
         n_w, n_t = n_img + 4, 60
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -379,8 +395,9 @@ def run_gpu_arm(args):
         from gsplat.dp import PipelinedTrainer
 
         scene_dev.update(fx=cams[0]["fx"], fy=cams[0]["fy"], cx=cams[0]["cx"], cy=cams[0]["cy"])
-        model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad, sh_layout="block")
-        trainer = PipelinedTrainer(model, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs, group=group)
+        model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad, sh_layout=_layout(args.operators))
+        trainer = PipelinedTrainer(model, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs, group=group,
+                                   operators=args.operators)
         torch.cuda.set_stream(trainer.main)  # everything below (events, prefetcher, timing) runs on the trainer's stream
     else:
         model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
@@ -480,28 +497,31 @@ def run_gpu_arm(args):
                "note": "per-step device time between consecutive events on the compute stream, max over ranks of each statistic"}
     value = world * 1000.0 / ms
 
-    # ---- the same step through the caller-modified fused operator, reported beside the drop-in number
-    fused_path = None
-    if not args.fused and not args.no_fused_path:
-        model_f = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)
-        trainer_f = ImageShardedTrainer(model_f, scene_dev, lr=1e-4, fused=True, sh_chunks=args.sh_chunks, optimizer=args.optimizer,
-                                        loss_fn=loss_fn)
-        fsteps = max(20, args.steps // 4)
-        for w in range(max(3, args.warmup // 2)):
-            trainer_f.train_step(cams[w % n_img], targets[w % n_img], w % n_img)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for k in range(fsteps):
-            trainer_f.train_step(cams[k % n_img], targets[k % n_img], k % n_img)
-        f1.record()
-        barrier()
-        tf = torch.tensor([f0.elapsed_time(f1) / fsteps], device=dev)
-        if world > 1:
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        fused_path = {"value": world * 1000.0 / float(tf.item()), "unit": "images/s", "ms_per_step": float(tf.item()),
-                      "steps": fsteps, "api": "gsplat.fused.render_gaussians (raw parameters in, one operator; caller-modified)"}
-        del trainer_f, model_f
+    # ---- the same trainer on the OTHER operator set (fused raw-parameter kernels <-> drop-in operators under autograd),
+    # reported beside the headline (one GPU only: it is an A/B of the per-GPU step, not of the exchange)
+    other_ops = None
+    if pipelined and world == 1 and not args.no_fused_path:
+        from gsplat.dp import PipelinedTrainer as _PT
+
+        other = "dropin" if args.operators == "fused" else "fused"
+        model_o = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad, sh_layout=_layout(other))
+        trainer_o = _PT(model_o, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs, operators=other)
+        osteps = max(40, args.steps // 4)
+        trainer_o.prepare(cam_rows[0], 0)
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_w = n_img + 4
+        for k in range(n_w + osteps):
+            if k == n_w:
+                trainer_o.finish()
+                o0.record()
+            trainer_o.train_step(targets[k % n_img], cam_rows[(k + 1) % n_img], (k + 1) % n_img)
+        trainer_o.finish()
+        o1.record()
+        torch.cuda.synchronize()
+        ms_o = o0.elapsed_time(o1) / osteps
+        other_ops = {"operators": other, "value": 1000.0 / ms_o, "unit": "images/s", "ms_per_step": ms_o, "steps": osteps,
+                     "api": _api(other)}
+        del trainer_o, model_o
 
     if args.timeline:  # every rank steps (collectives), rank 0 records
         from torch.profiler import ProfilerActivity, profile
@@ -763,7 +783,8 @@ def run_gpu_arm(args):
                     "optimizer": "gsplat.optim.FlatAdam (device step state)" if pipelined else ("gsplat.optim.FlatAdam (b200_adam_step)" if args.optimizer == "b200" else "torch.optim.Adam(fused=True)"),
                     "sh_chunks": args.sh_chunks, "loss": args.loss, "velocity_grad": vel_grad, "global_batch": world,
                     "api": ("gsplat.fused.render_gaussians (raw parameters, caller-modified)" if args.fused else
-                            "drop-in gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians"),
+                            _api(args.operators if pipelined else "dropin")),
+                    "operators": args.operators if pipelined else "dropin",
                     "parallelism": (f"image-sharded dp{world}" if args.mode == "image" else
                                     f"scene-sharded: {min(args.scenes, world)} independent scenes over {world} GPUs "
                                     f"(groups of {world // min(args.scenes, world)}-{-(-world // min(args.scenes, world))} ranks per scene, image-sharded inside a group)"),
@@ -776,8 +797,8 @@ def run_gpu_arm(args):
     }
     if ref_gpu:
         out["ref_gpu"] = ref_gpu
-    if fused_path:
-        out["fused_path"] = fused_path
+    if other_ops:
+        out["other_operators"] = other_ops
     if gpu_busy:
         out["gpu_busy"] = gpu_busy
     _emit(out)

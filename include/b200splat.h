@@ -231,6 +231,20 @@ B200_API int b200_fused_preprocess_forward(int num_points, const float *means, c
                                            float cy, unsigned img_height, unsigned img_width, unsigned block_width,
                                            float clip_thresh, void *packed, float *depths, int32_t *radii,
                                            int32_t *num_tiles_hit, void *stream);
+/* The forward in two halves, for a trainer that projects and bins image k+1 while the SH coefficients of step k are still
+ * being exchanged / updated (gsplat.dp.PipelinedTrainer): b200_fused_geometry_forward reads the geometry parameters only
+ * and leaves the records' colours 0; b200_fused_colors_forward fills clamp(SH colour + 0.5, 0) into the records of the
+ * Gaussians with radii > 0 afterwards (the binning does not read colours).  Together they write what
+ * b200_fused_preprocess_forward writes; b200_fused_preprocess_backward serves both. */
+B200_API int b200_fused_geometry_forward(int num_points, const float *means, const float *log_scales, const float *quats,
+                                         const float *opacity_logit, const float *viewmat, const float *lin_vel,
+                                         const float *ang_vel, float rolling_shutter_time, float exposure_time, float fx,
+                                         float fy, float cx, float cy, unsigned img_height, unsigned img_width,
+                                         unsigned block_width, float clip_thresh, void *packed, float *depths,
+                                         int32_t *radii, int32_t *num_tiles_hit, void *stream);
+B200_API int b200_fused_colors_forward(int num_points, const float *means, const float *sh_dc, const float *sh_rest,
+                                       int sh_bases, int degrees_to_use, const float *cam_pos, const int32_t *radii,
+                                       void *packed, void *stream);
 B200_API int b200_fused_preprocess_backward(int num_points, const float *means, const float *log_scales,
                                             const float *quats, const float *opacity_logit, const float *sh_dc,
                                             const float *sh_rest, int sh_bases, int degrees_to_use, const float *viewmat,

@@ -47,7 +47,7 @@ def _worker(rank, world, port, out, sh_chunks):
     dp.render = _fake_render
     scene = synthetic.make_scene("c1", n_override=50, n_cameras=4)
     model = dp.FlatGaussians(scene, "cpu", n_cameras=4, optimize_velocities=True)
-    assert model.flat.numel() == 50 * 59 + 24 and model.floats_per_gaussian == 59
+    assert model.flat.numel() == 50 * 59 + 24 + (-(50 * 11 + 24)) % 4 and model.floats_per_gaussian == 59  # SH rows 16-byte aligned
     # parameter views alias the flat buffer, gradient views alias the flat gradient buffer
     model.params["means"].data[0, 0] = 7.0
     assert model.flat[0] == 7.0
@@ -72,7 +72,7 @@ def _worker(rank, world, port, out, sh_chunks):
         tr2.train_step(cams[i], torch.zeros(scene["H"], scene["W"], 3), i)
     assert torch.allclose(model.flat.detach(), model2.flat.detach(), rtol=0, atol=1e-6)
     # layout: geometry + opacity rows, camera rows, then ONE contiguous SH block at the tail
-    assert model.slices["cam_vel"] == (50 * 11, 50 * 11 + 24) and model.sh_start == 50 * 11 + 24
+    assert model.slices["cam_vel"] == (50 * 11, 50 * 11 + 24) and model.sh_start == 50 * 11 + 24 + 2  # (+2: 16-byte grid)
     # camera-velocity rows are disjoint per image: rows of images nobody rendered this step keep zero grad
     last = {(2 * world + r) % 4 for r in range(world)}
     for c in range(4):

@@ -72,7 +72,8 @@ def test_densifier_matches_the_oracle(layout, step):
     assert dens.grad_norm is None and float(model.flat_grad.abs().max()) == 0.0
 
 
-def test_training_continues_across_a_refinement():
+@pytest.mark.parametrize("layout", ["block", "split"])
+def test_training_continues_across_a_refinement(layout):
     """PipelinedTrainer (CUDA graphs) -> statistics -> refine -> on_resize -> more steps on the new buffers."""
     import gsplat.synthetic as synthetic
     from gsplat.densify import DensifyConfig, Densifier
@@ -83,8 +84,9 @@ def test_training_continues_across_a_refinement():
     cams = sc["cameras"]
     for c in cams:
         c["target"] = c["target"][:128, :160].contiguous()
-    model = FlatGaussians(sc, "cuda", n_cameras=2, optimize_velocities=True, sh_layout="block")
+    model = FlatGaussians(sc, "cuda", n_cameras=2, optimize_velocities=True, sh_layout=layout)
     tr = PipelinedTrainer(model, sc, lr=1e-3, use_graphs=True)
+    assert tr.operators == ("fused" if layout == "split" else "dropin")   # split: the raw-parameter kernels
     cfg = DensifyConfig(warmup_length=0, refine_every=5, densify_grad_thresh=1e-7, reset_alpha_every=30)
     dens = Densifier(model, tr.adam, cfg, num_train_data=2)
     tr.after_backward = lambda absgrad, radii: dens.accumulate(absgrad, radii, 128, 160, step=tr.steps)

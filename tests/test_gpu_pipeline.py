@@ -173,11 +173,51 @@ def _trainer_scene(n=20000, n_cameras=3):
     return sc, cams
 
 
-@pytest.mark.parametrize("use_graphs", [False, True])
-def test_pipelined_trainer_matches_the_synchronising_trainer(use_graphs):
+@pytest.mark.parametrize("n", [20000, 20001])
+def test_fused_phases_match_the_dropin_phases(n):
+    """One image through the two phases of a pipelined step: on the fused raw-parameter kernels (fused_geometry_phase /
+    fused_shading_phase: no autograd graph, gradients written into the flat buffer by one kernel) and on the drop-in
+    operators under autograd -- same loss, same gradient buffer, same abs-grad statistic.  The odd Gaussian count puts the
+    quaternion rows off the 16-byte grid (scalar load / store path of the fused kernels)."""
+    from gsplat import dp
+    from gsplat.losses import l1_loss
+
+    outs = []
+    for fused in (False, True):
+        sc, cams = _trainer_scene(n=n)
+        m = dp.FlatGaussians(sc, "cuda", n_cameras=3, optimize_velocities=True, sh_layout="split" if fused else "block")
+        with torch.no_grad():
+            m.cam_vel.add_(0.01 * torch.randn(3, 6, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)))
+        c = cams[1]
+        st = dict(cam=torch.cat([c["viewmat"].reshape(-1)[:12], c["lin_vel"], c["ang_vel"], c["cam_pos"]]).float().cuda(),
+                  cam_index=torch.tensor([1], device="cuda"))
+        status = torch.zeros(4, dtype=torch.int32, device="cuda")
+        A, B = (dp.fused_geometry_phase, dp.fused_shading_phase) if fused else (dp.geometry_phase, dp.shading_phase)
+        geo = A(m, st, sc, 1 << 21, status)
+        loss = B(m, geo, sc, c["target"], l1_loss, 3)
+        absgrad = geo["absgrad"] if fused else geo["xys"].absgrad
+        grads = {k: m.flat_grad[a:b].clone() for k, (a, b) in m.slices.items()}
+        if not fused:
+            g = grads.pop("sh").view(m.N, m.K, 3)
+            grads["sh_dc"], grads["sh_rest"] = g[:, :1].reshape(-1), g[:, 1:].reshape(-1)
+        outs.append((float(loss), grads, absgrad, status.tolist(), geo["radii"].clone()))
+    (l0, g0, a0, s0, r0), (l1, g1, a1, s1, r1) = outs
+    assert s0 == s1 and s0[0] == 0 and s0[1] > 1000 and torch.equal(r0, r1)
+    assert abs(l0 - l1) <= 2e-6 * abs(l0)
+    assert set(g0) == set(g1)
+    for k in g0:
+        scale = float(g0[k].abs().max())
+        assert scale > 0, k
+        torch.testing.assert_close(g1[k], g0[k], rtol=2e-3, atol=2e-5 * scale, msg=lambda m_: f"{k}: {m_}")
+    torch.testing.assert_close(a1, a0, rtol=2e-3, atol=2e-5 * float(a0.abs().max()))
+
+
+@pytest.mark.parametrize("use_graphs,operators", [(False, "dropin"), (True, "dropin"), (False, "fused"), (True, "fused")])
+def test_pipelined_trainer_matches_the_synchronising_trainer(use_graphs, operators):
     """Six optimizer steps (two passes over three cameras): gsplat.dp.PipelinedTrainer (capacity-mode lists, device Adam
-    state, SH block layout + gradient sink, phase A of image k+1 queued before the SH update of step k; eager and as CUDA
-    graphs) ends at the same parameters as ImageShardedTrainer on the synchronising operators."""
+    state, phase A of image k+1 queued before the SH update of step k; eager and as CUDA graphs; on the drop-in operators
+    with the SH block layout + gradient sink, and on the fused raw-parameter kernels) ends at the same parameters as
+    ImageShardedTrainer on the synchronising operators."""
     from gsplat.dp import FlatGaussians, ImageShardedTrainer, PipelinedTrainer
 
     sc, cams = _trainer_scene()
@@ -187,8 +227,9 @@ def test_pipelined_trainer_matches_the_synchronising_trainer(use_graphs):
     for k in range(6):
         losses0.append(float(t0.train_step(cams[k % 3], cams[k % 3]["target"], k % 3)))
     sc, cams = _trainer_scene()
-    m1 = FlatGaussians(sc, "cuda", n_cameras=3, optimize_velocities=True, sh_layout="block")
-    t1 = PipelinedTrainer(m1, sc, lr=1e-3, use_graphs=use_graphs)
+    m1 = FlatGaussians(sc, "cuda", n_cameras=3, optimize_velocities=True, sh_layout="block" if operators == "dropin" else "split")
+    t1 = PipelinedTrainer(m1, sc, lr=1e-3, use_graphs=use_graphs, operators=None if operators == "fused" else operators)
+    assert t1.operators == operators
     losses1 = []
     t1.prepare(cams[0], 0)
     for k in range(6):
@@ -205,7 +246,8 @@ def test_pipelined_trainer_matches_the_synchronising_trainer(use_graphs):
         assert float((m0.params[k] - m1.params[k]).abs().max()) < 5e-4, k
     assert float((m0.cam_vel - m1.cam_vel).abs().max()) < 5e-4
     sh0 = torch.cat((m0.params["sh_dc"], m0.params["sh_rest"]), 1)
-    assert float((sh0 - m1.params["sh"]).abs().max()) < 5e-4  # Adam normalises: tiny gradient differences stay tiny steps
+    sh1 = m1.params["sh"] if operators == "dropin" else torch.cat((m1.params["sh_dc"], m1.params["sh_rest"]), 1)
+    assert float((sh0 - sh1).abs().max()) < 5e-4  # Adam normalises: tiny gradient differences stay tiny steps
 
 
 def test_pipelined_trainer_vetoes_an_overflowing_image_and_recovers():

@@ -14,7 +14,7 @@ python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ||
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/${TAG}_bench.json").read().strip().splitlines()[-1])
-print("bench", round(d["value"],1), round(d["ms_per_step"],4), d.get("step_ms"), "e2e", round(d["e2e"]["value"],1), "fused_path", (d.get("fused_path") or {}).get("value"), "launches", d["gpu_launches"], "cpu", (d.get("cpu_baseline") or {}).get("value"))
+print("bench", round(d["value"],1), round(d["ms_per_step"],4), d.get("step_ms"), "e2e", round(d["e2e"]["value"],1), "other_ops", (d.get("other_operators") or {}).get("value"), "launches", d["gpu_launches"], "cpu", (d.get("cpu_baseline") or {}).get("value"))
 print({k: v["ms"] for k, v in d["kernels"].items()})
 print(d["roofline"])
 PY
