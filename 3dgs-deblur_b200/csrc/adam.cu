@@ -167,9 +167,9 @@ extern "C" int b200_adam_prepare(void *state, int32_t *veto_flag, double lr, dou
 }
 
 // b200_adam_step with the step count / bias corrections / veto read from the device state prepared above.
-extern "C" int b200_adam_step_state(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
-                                    const void *state, double beta1, double beta2, double eps, double grad_scale,
-                                    int zero_grad, void *stream) {
+static int adam_state_launch(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq, const void *state,
+                             double beta1, double beta2, double eps, double grad_scale, int zero_grad, long long max_blocks,
+                             void *stream) {
     B200_REQUIRE(numel >= 0, "numel must be >= 0");
     if (numel == 0) return B200_OK;
     B200_REQUIRE(param && grad && exp_avg && exp_avg_sq && state, "null pointer");
@@ -183,10 +183,30 @@ extern "C" int b200_adam_step_state(long long numel, float *param, float *grad, 
     a.eps = (float)eps; a.grad_scale = (float)grad_scale; a.zero_grad = zero_grad ? 1 : 0;
     const long long n4 = numel >> 2;
     long long want = (n4 + ADAM_THREADS - 1) / ADAM_THREADS;
-    const long long cap = 1ll << 30;
-    const int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    const int blocks = (int)(want < 1 ? 1 : (want > max_blocks ? max_blocks : want));
     adam_state_kernel<<<blocks, ADAM_THREADS, 0, as_stream(stream)>>>(numel, param, grad, exp_avg, exp_avg_sq, a,
                                                                      static_cast<const AdamState *>(state));
     B200_LAUNCH_CHECK();
     return B200_OK;
+}
+
+extern "C" int b200_adam_step_state(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                                    const void *state, double beta1, double beta2, double eps, double grad_scale,
+                                    int zero_grad, void *stream) {
+    return adam_state_launch(numel, param, grad, exp_avg, exp_avg_sq, state, beta1, beta2, eps, grad_scale, zero_grad, 1ll << 30,
+                             stream);
+}
+
+// The same update as a BACKGROUND kernel: at most ctas_per_sm resident CTAs per SM looping over the slice, so that
+// kernels launched beside it on other streams (whatever their priority; memset nodes of a captured graph carry none)
+// always find free thread slots instead of queueing behind a grid of thousands of short CTAs.
+extern "C" int b200_adam_step_state_background(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                                               const void *state, double beta1, double beta2, double eps, double grad_scale,
+                                               int zero_grad, int ctas_per_sm, void *stream) {
+    B200_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 32, "ctas_per_sm must be in [1, 32]");
+    int dev = 0, sms = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return adam_state_launch(numel, param, grad, exp_avg, exp_avg_sq, state, beta1, beta2, eps, grad_scale, zero_grad,
+                             (long long)sms * ctas_per_sm, stream);
 }

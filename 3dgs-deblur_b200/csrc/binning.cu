@@ -674,7 +674,12 @@ static bool side_stream(SideStream &out) {
     std::lock_guard<std::mutex> lock(side_mu);
     if (!made[dev]) {
         SideStream s;
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        // highest priority: the forked section is on the caller's critical path whatever the caller's own priority is (a
+        // trainer that runs a bandwidth-bound update on a low-priority stream beside the binning would otherwise see this
+        // section queue behind that update's grid: r2o timeline, sort started 50 us late)
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return false;
+        if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
         if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return false;
         if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return false;
         per_dev[dev] = s;
@@ -685,6 +690,13 @@ static bool side_stream(SideStream &out) {
 }
 
 constexpr int CULL_GRID = 148 * 8;  // persistent warps, grid-stride over the chunk list
+// The counting pass runs beside the depth sort (side stream): 8 CTAs of 256 threads per SM would fill every thread slot
+// and the sort's kernels would only start as the count drains (r2n timeline: histogram 21 us late, the four onesweep
+// passes after the count) -- 6 per SM leave a quarter of each SM to the sort chain.
+#ifndef B200_CULL_COUNT_CTAS
+#define B200_CULL_COUNT_CTAS 6
+#endif
+constexpr int CULL_COUNT_GRID = 148 * B200_CULL_COUNT_CTAS;
 
 static CullGeom make_cull_geom(unsigned H, unsigned W, unsigned bw, unsigned S, float rs, float exposure) {
     CullGeom c;
@@ -746,7 +758,7 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     }
     B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, chunks, chunk_off, n, st));
     count_launch(2);
-    (c.per_sample ? cull_chunks_kernel<false, true> : cull_chunks_kernel<false, false>)<<<CULL_GRID, 256, 0, st>>>(
+    (c.per_sample ? cull_chunks_kernel<false, true> : cull_chunks_kernel<false, false>)<<<CULL_COUNT_GRID, 256, 0, st>>>(
         n, 0, rec, bbox, chunk_off, chunks, c, counters, masks, L.mask_cap, survivors, nullptr, nullptr, nullptr, nullptr, 0u, nullptr);
     B200_LAUNCH_CHECK();
     // (a later record of the shared join event by another caller is ordered after this one on the side stream)

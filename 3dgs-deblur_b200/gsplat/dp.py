@@ -18,6 +18,7 @@ splatfacto.py:417-434) are exposed by `reduce_densify_stats` with the matching s
 reductions so a caller can keep topology changes identical across ranks.
 """
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -454,10 +455,14 @@ def fused_shading_phase(model: FlatGaussians, geo: Dict, scene: Dict, target: to
         check(lib.b200_fused_colors_forward(n, ptr(p["means"]), ptr(p["sh_dc"]), ptr(p["sh_rest"]), K, sh_degree_to_use,
                                             ptr(cam_pos), ptr(radii), ptr(packed), stream()))
         rgb, Ts, fi = _C.blend_forward_packed(H, W, bw, S, geo["ids"], geo["bins"], packed, rs, ex, bg, status=geo["status"])
-    rgb.requires_grad_(True)
-    with torch.enable_grad():
-        loss = loss_fn(rgb, target)
-    (v_rgb,) = torch.autograd.grad(loss, rgb)
+    from gsplat.losses import l1_loss, l1_loss_and_grad
+    if loss_fn is l1_loss:  # the default: value and cotangent from the one kernel
+        loss, v_rgb = l1_loss_and_grad(rgb, target)
+    else:
+        rgb.requires_grad_(True)
+        with torch.enable_grad():
+            loss = loss_fn(rgb, target)
+        (v_rgb,) = torch.autograd.grad(loss, rgb)
     with torch.no_grad(), _lib.on_device(dev):
         v_xy, v_abs, v_pix, v_conic, v_col, v_op = _C.blend_backward_packed(
             n, H, W, bw, S, geo["ids"], geo["bins"], packed, rs, ex, bg, Ts, fi, v_rgb, None)
@@ -569,6 +574,10 @@ class PipelinedTrainer:
         self._flag_work = None
         self._pending_sh = None
         self.optimizer = optimizer
+        # SH update launch shape (measured at c2, 1 GPU, r2q: resident-CTA-limited background kernels were SLOWER -- 1.33 ms
+        # per step with 1-2 CTAs per SM against 1.30 with one short CTA per 256 vectors -- so 0 = short CTAs is the default)
+        self.sh_update_ctas = int(os.environ.get("B200_SH_UPDATE_CTAS", "0"))
+        self.sh_update_pieces = int(os.environ.get("B200_SH_UPDATE_PIECES", "8"))
         # the SH block is exchanged in `sh_chunks` pieces so that the update of piece i runs while piece i+1 is on the wire
         lo, total = model.sh_start, model.flat.numel()
         n_sh = max(1, int(sh_chunks)) if self.distributed else 1
@@ -592,8 +601,10 @@ class PipelinedTrainer:
             # after each call).  Autograd ties every leaf's gradient accumulation to the stream that was current when the
             # accumulator was first used; if that were the legacy default stream, the backward pass inside a graph capture
             # would have to synchronise with it, which invalidates the capture.
-            self.main = torch.cuda.Stream(device=dev)
-            self.side = torch.cuda.Stream(device=dev)
+            # `main` outranks `side`: the SH update (one bandwidth-bound kernel of many short CTAs) then fills the SMs the
+            # next image's projection / binning kernels leave idle instead of queueing its whole grid ahead of them
+            self.main = torch.cuda.Stream(device=dev, priority=-1)
+            self.side = torch.cuda.Stream(device=dev, priority=0)
             model.rebind_leaves()  # gradient accumulators are (re)created on `main` by the first step
             self.ev_prepared, self.ev_sh_done, self.ev_poll = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
             self._host_words = torch.zeros(2, 24, dtype=torch.int32).pin_memory()   # status (4) | adam state (16) | quat flag
@@ -803,7 +814,18 @@ class PipelinedTrainer:
 
     def _update(self, a, b_, scale, veto_host, which):
         if self.adam is not None:
-            self.adam.update_state(a, b_, scale, True)
+            if which == 1 and self.sh_update_pieces > 1:
+                # the SH slice is updated on the side stream beside the next image's projection / binning.  One launch would
+                # queue its whole grid (tens of thousands of short CTAs) ahead of whatever arrives later at the same
+                # priority -- the memset nodes of the binning graph carry none, r2p timeline: the depth sort waited 31 us
+                # for one -- so it goes out in pieces: a late arrival waits for one piece at most
+                n = self.sh_update_pieces
+                cuts = [a + ((b_ - a) * k // n) // 4 * 4 for k in range(n)] + [b_]
+                for lo_, hi_ in zip(cuts[:-1], cuts[1:]):
+                    if hi_ > lo_:
+                        self.adam.update_state(lo_, hi_, scale, True, background_ctas=self.sh_update_ctas)
+                return
+            self.adam.update_state(a, b_, scale, True, background_ctas=self.sh_update_ctas if which == 1 else 0)
             return
         g = self.model.flat_grad[a:b_]
         if not veto_host:

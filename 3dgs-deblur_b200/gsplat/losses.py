@@ -66,6 +66,19 @@ def l1_loss(pred: torch.Tensor, target: torch.Tensor, gamma: float = None) -> to
     return _L1Loss.apply(pred, target, gamma)
 
 
+def l1_loss_and_grad(pred: torch.Tensor, target: torch.Tensor, gamma: float = None):
+    """(mean |pred - target|, d loss / d pred) from the one kernel, outside autograd -- for callers that chain the
+    cotangent themselves (gsplat.dp.fused_shading_phase).  Same arguments and checks as `l1_loss`."""
+    with torch.no_grad():
+        ctx = _Ctx()
+        loss = _L1Loss.forward(ctx, pred, target, gamma)
+    return loss, ctx.grad
+
+
+class _Ctx:
+    needs_input_grad = (True, False, False)
+
+
 # ---- SSIM and the full photometric loss (splatfacto.py:957-975) -------------------------------------------------
 
 _ssim_ws = {}

@@ -41,16 +41,24 @@ class FlatAdam:
             check(self._lib.b200_adam_prepare(self.state.data_ptr(), None if veto_flag is None else veto_flag.data_ptr(),
                                               self.lr, self.betas[0], self.betas[1], stream()))
 
-    def update_state(self, begin: int = 0, end: int = None, grad_scale: float = 1.0, zero_grad: bool = True):
+    def update_state(self, begin: int = 0, end: int = None, grad_scale: float = 1.0, zero_grad: bool = True,
+                     background_ctas: int = 0):
+        """background_ctas > 0: run as a background kernel with that many resident CTAs per SM
+        (b200_adam_step_state_background) -- for an update queued on a second stream beside latency-bound kernels."""
         end = self.flat.numel() if end is None else end
         if not (0 <= begin <= end <= self.flat.numel()) or begin % 4:
             raise ValueError(f"FlatAdam.update_state: bad slice [{begin}, {end}) (must start on a 16-byte boundary)")
         off = 4 * begin
         p, g, m, v = self._ptrs
         with _lib.on_device(self.flat.device):
-            check(self._lib.b200_adam_step_state(end - begin, p + off, g + off, m + off, v + off, self.state.data_ptr(),
-                                                 self.betas[0], self.betas[1], self.eps, float(grad_scale),
-                                                 1 if zero_grad else 0, stream()))
+            if background_ctas > 0:
+                check(self._lib.b200_adam_step_state_background(
+                    end - begin, p + off, g + off, m + off, v + off, self.state.data_ptr(), self.betas[0], self.betas[1],
+                    self.eps, float(grad_scale), 1 if zero_grad else 0, int(background_ctas), stream()))
+            else:
+                check(self._lib.b200_adam_step_state(end - begin, p + off, g + off, m + off, v + off, self.state.data_ptr(),
+                                                     self.betas[0], self.betas[1], self.eps, float(grad_scale),
+                                                     1 if zero_grad else 0, stream()))
 
     def rebind(self, flat: torch.Tensor, flat_grad: torch.Tensor):
         """The parameter buffers were reallocated (densification): fresh zero moments of the new size; the caller fills them

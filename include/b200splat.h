@@ -336,6 +336,12 @@ B200_API int b200_adam_prepare(void *state, int32_t *veto_flag, double lr, doubl
 B200_API int b200_adam_step_state(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
                                   const void *state, double beta1, double beta2, double eps, double grad_scale,
                                   int zero_grad, void *stream);
+/* The same update as a background kernel for a caller that runs it on a second stream beside latency-bound work: at most
+ * ctas_per_sm (1..32) resident CTAs of 256 threads per SM loop over the slice, so kernels launched beside it always find
+ * free thread slots instead of queueing behind a grid of thousands of short CTAs.  Same arithmetic, same result. */
+B200_API int b200_adam_step_state_background(long long numel, float *param, float *grad, float *exp_avg, float *exp_avg_sq,
+                                             const void *state, double beta1, double beta2, double eps, double grad_scale,
+                                             int zero_grad, int ctas_per_sm, void *stream);
 
 /* ---- rasterization without a host sync ---------------------------------------------------------------------------
  * The reference reads the intersection count back to size its lists (gsplat/utils.py:123-124 `.item()`); the two-phase
