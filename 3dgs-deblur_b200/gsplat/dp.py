@@ -528,7 +528,7 @@ class PipelinedTrainer:
 
     def __init__(self, model: FlatGaussians, scene: Dict, lr: float = 1e-3, group=None, loss_fn=None, use_graphs: bool = True,
                  capacity: Optional[int] = None, sh_degree_to_use: int = 3, geometry_fn=None, shading_fn=None,
-                 optimizer: str = "b200", sh_chunks: int = 2, operators: Optional[str] = None):
+                 optimizer: str = "b200", sh_chunks: int = 1, operators: Optional[str] = None):
         """operators: "dropin" = the two phases on the reference-compatible operators under autograd (`geometry_phase` /
         `shading_phase`); "fused" = on the fused raw-parameter kernels (`fused_geometry_phase` / `fused_shading_phase`:
         same numbers, ~45 fewer launches per step); None = fused where it applies (CUDA, sh_layout "split"), else drop-in."""

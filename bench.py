@@ -84,11 +84,12 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="override the Gaussian count (debug only)")
     ap.add_argument("--no-vel-grad", action="store_true", help="camera velocities constant (reference CUDA-path mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--images", type=int, default=8, help="distinct training images per rank")
+    ap.add_argument("--images", type=int, default=16, help="distinct training images per rank (N > 1: the cost-aware batching groups 16 x N images; more images = tighter groups)")
     ap.add_argument("--profile", action="store_true", help="also report the summed device time of all kernels per step (CUPTI)")
     ap.add_argument("--loss", default="l1", choices=["l1", "photometric"],
                     help="l1 = BASELINE's loss; photometric = Splatfacto's 0.8 L1 + 0.2 (1 - SSIM) through the fused kernels")
-    ap.add_argument("--sh-chunks", type=int, default=1, help="pieces of the SH block in the gradient exchange (N > 1)")
+    ap.add_argument("--sh-chunks", type=int, default=None,
+                    help="pieces of the SH block in the gradient exchange (N > 1); default 1 (measured at N=4, c2: one 57.6 MB allreduce 163 us, two halves 2 x 115 us)")
     ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"], help="FlatAdam kernel or torch's fused Adam")
     ap.add_argument("--no-fused-path", action="store_true", help="skip the extra fused-operator measurement")
     ap.add_argument("--mode", default="image", choices=["image", "scene"],
@@ -111,7 +112,10 @@ def parse():
     ap.add_argument("--no-graphs", action="store_true", help="pipelined trainer without CUDA-graph capture (debug / A-B)")
     ap.add_argument("--fused", action="store_true",
                     help="render through gsplat.fused.render_gaussians (caller-modified 'next' path) instead of the drop-in operators")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.sh_chunks is None:
+        args.sh_chunks = 1
+    return args
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -397,7 +401,7 @@ def run_gpu_arm(args):
         scene_dev.update(fx=cams[0]["fx"], fy=cams[0]["fy"], cx=cams[0]["cx"], cy=cams[0]["cy"])
         model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad, sh_layout=_layout(args.operators))
         trainer = PipelinedTrainer(model, scene_dev, lr=1e-4, loss_fn=loss_fn, use_graphs=not args.no_graphs, group=group,
-                                   operators=args.operators)
+                                   operators=args.operators, sh_chunks=args.sh_chunks)
         torch.cuda.set_stream(trainer.main)  # everything below (events, prefetcher, timing) runs on the trainer's stream
     else:
         model = FlatGaussians(scene_dev, dev, n_cameras=n_img, optimize_velocities=vel_grad)

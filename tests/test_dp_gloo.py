@@ -166,7 +166,8 @@ def _pipelined_worker(rank, world, port, out):
     m1 = dp.FlatGaussians(scene, "cpu", n_cameras=4, optimize_velocities=True, sh_layout="block")
     assert m1.sh_start % 4 == 0 and m1.params["sh"].shape == (50, 16, 3)
     t1 = dp.PipelinedTrainer(m1, scene, lr=1e-2, loss_fn=_torch_l1, optimizer="torch", geometry_fn=_fake_geometry,
-                             shading_fn=_fake_shading, capacity=1)
+                             shading_fn=_fake_shading, capacity=1, sh_chunks=2)  # (two SH pieces: the chunked exchange path)
+    assert len(t1._sh_bounds) == 2
     order = [t0.image_index(s, 4) for s in range(4)]
     t1.prepare(_cam_row(order[0] + 1), order[0])
     for step in range(4):
