@@ -19,7 +19,7 @@ print({k: v["ms"] for k, v in d["kernels"].items()})
 print(d["roofline"])
 PY
 if [ "$MODE" != "quick" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-fused-path > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-fused-path --no-ref-gpu > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:blend_backward_kernel -c 1 -o gpurun_out/prof_bwd_${TAG} -f python tools/blend_probe.py --reps 1 --what bwd > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:blend_forward_kernel -c 1 -o gpurun_out/prof_fwd_${TAG} -f python tools/blend_probe.py --reps 1 --what fwd > /dev/null 2>&1
 fi
