@@ -279,6 +279,13 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
 //   * sigma, exp, alpha for both pixels in straight-line code; pixels that fail a test are masked by zeroing `vis` and
 //     `alpha` (then fac, v_sigma and every accumulated term are exactly 0 and T is kept by a select) -- one vote decides
 //     whether the gradient algebra runs at all.
+// Visit epilogue of the packed kernel: the 13 per-Gaussian sums are reduced over the warp through a shared-memory
+// transposition (B200_BWD_SMEM_REDUCE=1, default) or with the 16-shuffle transposing butterfly above (=0, A/B build).
+#ifndef B200_BWD_SMEM_REDUCE
+#define B200_BWD_SMEM_REDUCE 1
+#endif
+constexpr int RED_VALUES = 13;  // rgb 3, conic 3, xy 2, |xy| 2, pixel velocity 2, opacity 1
+constexpr int RED_STRIDE = 36;  // floats per row: 32 lanes + 4 of padding (rows stay 16-byte aligned, halves hit distinct banks)
 #ifndef B200_BWD_MIN_CTAS
 #define B200_BWD_MIN_CTAS 5  // 96 registers; A/B of 4 / 6 in DESIGN.md section 9
 #endif
@@ -288,6 +295,9 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
     __shared__ __align__(8) uint64_t s_bar[BLEND_STAGES];
     __shared__ int s_max[NT / 32];
+#if B200_BWD_SMEM_REDUCE
+    __shared__ __align__(16) float s_red[NT / 32][RED_VALUES * RED_STRIDE];  // per-warp transposition buffer (visit epilogue)
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -376,6 +386,13 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
             else if (k == 12) { my_dst = p.v_opac; my_stride = 1; }
         }
     }
+
+#if B200_BWD_SMEM_REDUCE
+    float *const red_row = &s_red[warp][lane];
+    // lanes 26..31 own no sum (my_dst is null): they re-read row 12 (a broadcast) instead of branching
+    const ulonglong2 *const red_half =
+        reinterpret_cast<const ulonglong2 *>(&s_red[warp][min(lane >> 1, RED_VALUES - 1) * RED_STRIDE + (lane & 1) * 16]);
+#endif
 
     auto issue = [&](int b) {
         const int st = b & 1;
@@ -475,10 +492,39 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                     }
                     if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
                     if (lane == 0) B200_COUNT(5, 1);
+#if B200_BWD_SMEM_REDUCE
+                    // lane l parks value j at row j, column l (bank 4 j + l: conflict free); lanes 2 j and 2 j + 1 then add up
+                    // the two halves of row j with 4 LDS.128 + 7 packed adds each and meet in one shuffle.  Same owner lane
+                    // (2 j) per sum as the butterfly, 13 STS + 4 LDS + 1 SHFL instead of 16 SHFL + 27 selects.
+                    red_row[0 * RED_STRIDE] = f2_sum(f2_mul(facsum, VO0));
+                    red_row[1 * RED_STRIDE] = f2_sum(f2_mul(facsum, VO1));
+                    red_row[2 * RED_STRIDE] = f2_sum(f2_mul(facsum, VO2));
+                    red_row[3 * RED_STRIDE] = 0.5f * f2_sum(sxx);
+                    red_row[4 * RED_STRIDE] = f2_sum(sxy);
+                    red_row[5 * RED_STRIDE] = 0.5f * f2_sum(syy);
+                    red_row[6 * RED_STRIDE] = f2_sum(gxs);
+                    red_row[7 * RED_STRIDE] = f2_sum(gys);
+                    red_row[8 * RED_STRIDE] = gxa;
+                    red_row[9 * RED_STRIDE] = gya;
+                    red_row[10 * RED_STRIDE] = f2_sum(pvx);
+                    red_row[11 * RED_STRIDE] = f2_sum(pvy);
+                    red_row[12 * RED_STRIDE] = f2_sum(vop);
+                    __syncwarp();
+                    float tot;
+                    {
+                        const ulonglong2 q0 = red_half[0], q1 = red_half[1], q2 = red_half[2], q3 = red_half[3];
+                        const f2 a0 = f2_add(f2{q0.x}, f2{q0.y}), a1 = f2_add(f2{q1.x}, f2{q1.y});
+                        const f2 a2 = f2_add(f2{q2.x}, f2{q2.y}), a3 = f2_add(f2{q3.x}, f2{q3.y});
+                        tot = f2_sum(f2_add(f2_add(a0, a1), f2_add(a2, a3)));
+                    }
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                    __syncwarp();  // every lane has read its half before the next visit overwrites the rows
+#else
                     const float v[16] = {f2_sum(f2_mul(facsum, VO0)), f2_sum(f2_mul(facsum, VO1)), f2_sum(f2_mul(facsum, VO2)),
                                          0.5f * f2_sum(sxx), f2_sum(sxy), 0.5f * f2_sum(syy), f2_sum(gxs), f2_sum(gys), gxa, gya,
                                          f2_sum(pvx), f2_sum(pvy), f2_sum(vop), 0.f, 0.f, 0.f};
                     const float tot = butterfly16(v, lane);
+#endif
                     if (my_dst && tot != 0.f) {
                         const int gid = s_rec[st][k].id;
                         atomicAdd(my_dst + (unsigned)gid * (unsigned)my_stride, tot);  // N * 3 < 2^32

@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200_l1_loss_ws_bytes": (_sz, []),
     "b200_l1_loss": (_i, [C.c_longlong, _p, _p, _p, _p, _p, _i, _p]),
     "b200_l1_loss_gamma": (_i, [C.c_longlong, _p, _p, _f, _p, _p, _p, _i, _p]),
+    "b200_l1_loss_u8": (_i, [C.c_longlong, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _p]),
     "b200_nd_rasterize_forward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200_nd_rasterize_backward": (_i, [_i, _u, _u, _u, _u, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                         _p, _p, _p, _p, _p, _p]),

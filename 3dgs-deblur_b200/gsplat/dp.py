@@ -696,14 +696,22 @@ class PipelinedTrainer:
             g = torch.cuda.CUDAGraph()
             n0 = self._lib_launches()
             with torch.cuda.graph(g, stream=self.main):
-                tgt = e["target"].float() / 255 if e["target"].dtype == torch.uint8 else e["target"]
+                tgt = self._as_target(e["target"])
                 self.loss.copy_(self.shading_fn(self.model, e["geo"], self.scene, tgt, self.loss_fn, self.sh_degree))
             e["gB"], e["nB"] = g, self._lib_launches() - n0
             g.replay()
             return
-        tgt = target.float() / 255 if target.dtype == torch.uint8 else target
+        tgt = self._as_target(target)
         self.loss.copy_(self.shading_fn(self.model, self._geo, self.scene, tgt, self.loss_fn, self.sh_degree))
         e["warm"] += 1
+
+    def _as_target(self, target):
+        """The dataset's uint8 image goes to the loss as it is when the loss converts it in its own kernel
+        (gsplat.losses.l1_loss / photometric_loss); any other loss gets the float image the reference builds
+        (get_gt_img, splatfacto.py:906-907)."""
+        if target.dtype != torch.uint8 or getattr(self.loss_fn, "accepts_uint8", False):
+            return target
+        return target.float() / 255
 
     # ---- public API ----------------------------------------------------------------------------------------------
     class _OnMain:

@@ -25,9 +25,15 @@ def render_gaussians(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_l
                      angular_velocity: Optional[Tensor], fx: float, fy: float, cx: float, cy: float, img_height: int,
                      img_width: int, block_width: int, background: Tensor, rolling_shutter_time: float = 0.0,
                      exposure_time: float = 0.0, blur_samples: int = 1, sh_degree_to_use: int = 3,
-                     clip_thresh: float = 0.01, grad_sink: Optional[Dict[str, Tensor]] = None):
+                     clip_thresh: float = 0.01, grad_sink: Optional[Dict[str, Tensor]] = None, return_depth: bool = False):
     """Returns (rgb (H,W,3), alpha (H,W), info).  info["radii"] (N,) int32; after backward info["absgrad"] (N,2) holds the
     abs-grad densification statistic (the `xys.absgrad` side channel of the drop-in operator).
+
+    return_depth: also info["depth"] (H,W,1), the caller's eval depth image (splatfacto.py:881-897: a second, static
+    rasterize call with the depths as colours over a zero background, divided by alpha; the largest rendered depth where
+    alpha is 0) -- one more blend launch over the lists already built instead of a second projection-sized binning
+    (lists are rebuilt only when the colour pass had rolling shutter or an even sample count with exposure: then they do
+    not provably contain the static lists).  Not differentiable.
 
     grad_sink (optional): {"means", "log_scales", "quats", "opacity_logit", "sh_dc", "sh_rest"} -> preallocated
     gradient buffers (e.g. slices of a flat DP buffer).  When given, backward OVERWRITES them directly (every row,
@@ -41,7 +47,27 @@ def render_gaussians(means: Tensor, log_scales: Tensor, quats: Tensor, opacity_l
                                     (float(fx), float(fy), float(cx), float(cy), int(img_height), int(img_width),
                                      int(block_width), float(rolling_shutter_time), float(exposure_time),
                                      int(blur_samples), int(sh_degree_to_use), float(clip_thresh)), grad_sink, info)
+    lists = info.pop("_lists")
+    if return_depth:
+        info["depth"] = _depth_pass(lists, alpha, int(img_height), int(img_width), int(block_width), int(blur_samples),
+                                    float(rolling_shutter_time), float(exposure_time))
     return rgb, alpha, info
+
+
+def _depth_pass(lists, alpha, H, W, bw, S, rs, ex):
+    packed, depths, radii, nth, ids, bins, total = lists
+    dev = depths.device
+    with torch.no_grad(), _lib.on_device(dev):
+        if total < 1:  # the reference's empty-render branch returns the (zero) background
+            depth_im = torch.zeros(H, W, 1, device=dev)
+        else:
+            rec = _C.set_record_colors(packed.clone(), depths[:, None].expand(-1, 3).contiguous())
+            if not (rs == 0 and (ex == 0 or S % 2 == 1)):  # see gsplat.rasterize: the static lists may hold other pairs
+                _, ids, bins = _C.bin_cull(rec, depths, radii, nth, H, W, bw, 1, 0.0, 0.0)
+            img, _, _ = _C.blend_forward_packed(H, W, bw, 1, ids, bins, rec, 0.0, 0.0, torch.zeros(3, device=dev))
+            depth_im = img[..., 0:1]
+        a = alpha.detach()[..., None]
+        return torch.where(a > 0, depth_im / a, depth_im.max())
 
 
 class _FusedRender(Function):
@@ -88,6 +114,7 @@ class _FusedRender(Function):
         ctx.save_for_backward(means, log_scales, quats, opacity_logit, sh_dc, sh_rest, viewmat, cam_pos, lin_d, ang_d, bg,
                               packed, radii, ids, bins, Ts, fi)
         info["radii"] = radii
+        info["_lists"] = (packed, depths, radii, nth, ids, bins, total)  # for render_gaussians' optional depth pass
         ctx.mark_non_differentiable(radii)
         ctx.set_materialize_grads(False)  # an unused alpha (or rgb) arrives as None instead of a zero image
         return rgb, alpha

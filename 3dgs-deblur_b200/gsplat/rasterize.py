@@ -27,6 +27,45 @@ def _prepare(xys, colors, background, block_width):
     return colors, background
 
 
+# ---- list reuse for the caller's second, static pass ------------------------------------------------------------------
+# In eval (and with `output_depth_during_training`) Splatfacto rasterizes the SAME projection twice: the colour image with
+# blur / rolling shutter, then depth as colours without them (splatfacto.py:860-897).  The reference bins twice.  Here the
+# second call reuses the first call's culled lists when they provably contain the static lists: same per-Gaussian
+# tensors (storage + version counter), same image / tile size, first call without rolling shutter and with either no
+# exposure or an ODD sample count (the middle sample's offset is exactly 0, so "can reach a tile at tau = 0" is one of
+# the tests the first cull kept entries for).  Extra entries are skipped by the blend's own alpha test, the order is the
+# reference's, so the image equals the one from freshly built lists bit for bit (tests/test_gpu_parity.py).
+# B200SPLAT_NO_LIST_REUSE=1 switches it off.
+_last_lists = {}  # device index -> dict(tensors=..., geom=..., blur=..., n_isect, ids, bins)
+
+
+def _same_tensor(a, b):
+    return a.data_ptr() == b.data_ptr() and a._version == b._version and a.shape == b.shape and a.dtype == b.dtype
+
+
+def _remember_lists(per_gaussian, geom, blur, n_isect, ids, bins):
+    import os
+    if os.environ.get("B200SPLAT_NO_LIST_REUSE") == "1":
+        return
+    # detached aliases keep the storages alive (an address can then not be handed to another tensor) without holding
+    # the autograd graph; the version counter is shared with the caller's tensor
+    _last_lists[per_gaussian[0].device.index] = dict(tensors=[t.detach() for t in per_gaussian], geom=geom, blur=blur,
+                                                     n_isect=n_isect, ids=ids, bins=bins)
+
+
+def _reusable_lists(per_gaussian, geom, n_samples, rs, ex):
+    """(n_isect, ids, bins) of the previous RGB call on this device if they cover a static pass over the same projection."""
+    c = _last_lists.get(per_gaussian[0].device.index)
+    if c is None or n_samples != 1 or rs != 0 or ex != 0 or c["geom"] != geom:
+        return None
+    S0, rs0, ex0 = c["blur"]
+    if rs0 != 0 or not (ex0 == 0 or S0 % 2 == 1):
+        return None
+    if not all(_same_tensor(a, b) for a, b in zip(per_gaussian, c["tensors"])):
+        return None
+    return c["n_isect"], c["ids"], c["bins"]
+
+
 class PreparedLists:
     """Tile lists of one image built ahead of the shading (`prepare_lists`): the packed records (colours still to be
     patched in), the culled id lists at a caller-chosen capacity, the tile ranges and the device status block."""
@@ -121,8 +160,17 @@ class _RasterizeGaussians(Function):
             if not (0 < n_samples <= _MAX_BLUR_SAMPLES):
                 raise RuntimeError("unsupported blur size")
             packed = _C.pack_records(xys, pix_vels, conics, colors, opacity)
-            n_isect, ids_sorted, tile_bins = _C.bin_cull(packed, depths, radii, num_tiles_hit, H, W, bw, n_samples,
-                                                         rolling_shutter_time, exposure_time)
+            # everything the cull reads (centres, extents via conics + opacity, velocities, depth order, tile counts)
+            binned = (xys, depths, pix_vels, radii, conics, num_tiles_hit, opacity)
+            geom = (int(H), int(W), int(bw))
+            reuse = _reusable_lists(binned, geom, n_samples, float(rolling_shutter_time), float(exposure_time))
+            if reuse is not None:
+                n_isect, ids_sorted, tile_bins = reuse
+            else:
+                n_isect, ids_sorted, tile_bins = _C.bin_cull(packed, depths, radii, num_tiles_hit, H, W, bw, n_samples,
+                                                             rolling_shutter_time, exposure_time)
+                _remember_lists(binned, geom, (n_samples, float(rolling_shutter_time), float(exposure_time)), n_isect,
+                                ids_sorted, tile_bins)
         else:
             n_isect, _ = compute_cumulative_intersects(num_tiles_hit)
 

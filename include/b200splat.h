@@ -288,6 +288,15 @@ B200_API int b200_l1_loss(long long numel, const float *pred, const float *targe
  * the linear image (torch's clamp / pow backward: (1/gamma) x^(1/gamma - 1) up to and including x = 1, 0 above, infinite at 0). */
 B200_API int b200_l1_loss_gamma(long long numel, const float *pred_linear, const float *target, float gamma, float *loss,
                                 float *grad_linear, void *ws, int ws_is_zeroed, void *stream);
+/* The same against the dataset's uint8 image with the caller's ground-truth preparation folded in: uint8 -> float / 255
+ * (splatfacto.py:900-910 get_gt_img), RGBA composited over `background` (3 DEVICE floats; :912-923 composite_with_background,
+ * alpha * rgb + (1 - alpha) * background, unfused like torch), clamp(min = min_level) with min_level = min_rgb_level / 255
+ * (:952-953; <= 0: off), optional mask (n_pixels floats: gt * mask, pred * mask, :957-964), L1 mean over 3 * n_pixels (:966).
+ * channels = 3 or 4; gamma > 0 applies the gamma step to pred as in b200_l1_loss_gamma, <= 0: pred is used as it is;
+ * target_out (3 * n_pixels floats or null) receives the prepared float target (what the SSIM term is taken against). */
+B200_API int b200_l1_loss_u8(long long n_pixels, int channels, const float *pred, const unsigned char *target_u8,
+                             const float *background, float min_level, float gamma, const float *mask, float *loss,
+                             float *grad, float *target_out, void *ws, int ws_is_zeroed, void *stream);
 
 /* SSIM term of the photometric loss, (1 - lambda) * L1 + lambda * (1 - SSIM) (nerfstudio/models/splatfacto.py:957-975;
  * SSIM = pytorch_msssim.SSIM(data_range=1, size_average=True, channel=C): 11-tap Gaussian window sigma 1.5, separable,

@@ -175,3 +175,74 @@ def test_trainer_with_flat_adam_matches_torch_adam():
         outs.append(model.flat.detach().clone())
     moved = (outs[0] - outs[1]).abs().max()
     assert float(moved) < 5e-4, float(moved)
+
+
+def _depth_chain(sc, cam, lv, reuse):
+    """Splatfacto's eval render (splatfacto.py:860-897): colour pass, then depth as colours in a second, static call."""
+    import os
+
+    import gsplat.rasterize as R
+    from gsplat import project_gaussians, rasterize_gaussians, spherical_harmonics
+
+    R._last_lists.clear()
+    os.environ["B200SPLAT_NO_LIST_REUSE"] = "0" if reuse else "1"
+    try:
+        with torch.no_grad():
+            H, W = sc["H"], sc["W"]
+            q = lv["quats"] / lv["quats"].norm(dim=-1, keepdim=True)
+            xys, depths, pv, radii, conics, comp, nth, _ = project_gaussians(
+                lv["means"], torch.exp(lv["log_scales"]), 1, q, lv["lin"], lv["ang"], sc["rolling_shutter_time"], sc["exposure_time"],
+                lv["viewmat"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], H, W, 16)
+            rgbs = torch.clamp(spherical_harmonics(3, lv["means"] - cam["cam_pos"], torch.cat((lv["sh_dc"], lv["sh_rest"]), dim=1)) + 0.5, min=0.0)
+            opac = torch.sigmoid(lv["opacity_logit"]) * comp[:, None]
+            S = sc["blur_samples"] if sc["exposure_time"] > 0 else 1
+            rgb, alpha = rasterize_gaussians(xys, depths, pv, radii, conics, nth, rgbs, opac, H, W, 16, background=lv["bg"],
+                                             return_alpha=True, rolling_shutter_time=sc["rolling_shutter_time"],
+                                             exposure_time=sc["exposure_time"], blur_samples=S)
+            cached = R._last_lists.get(xys.device.index)
+            depth_im = rasterize_gaussians(xys, depths, pv, radii, conics, nth, depths[:, None].repeat(1, 3), opac, H, W, 16,
+                                           background=torch.zeros(3, device="cuda"))[..., 0:1]
+            reused = cached is not None and R._last_lists.get(xys.device.index) is cached  # a fresh binning replaces the entry
+            alpha = alpha[..., None]
+            depth = torch.where(alpha > 0, depth_im / alpha, depth_im.detach().max())
+        return rgb, alpha, depth, depth_im, reused, dict(xys=xys, depths=depths, radii=radii, conics=conics, nth=nth, opac=opac)
+    finally:
+        os.environ.pop("B200SPLAT_NO_LIST_REUSE", None)
+
+
+@pytest.mark.parametrize("S,rs,ex,expect_reuse", [(5, 0.0, 1 / 60, True), (4, 0.0, 1 / 60, False), (5, 1 / 50, 1 / 60, False),
+                                                  (1, 0.0, 0.0, True)])
+def test_depth_pass_list_reuse_and_fused_depth(S, rs, ex, expect_reuse):
+    """The caller's static depth pass over the colour pass's lists (gsplat.rasterize list reuse, gsplat.fused
+    return_depth): bit-identical to freshly built lists, equal to the oracle's static render of the depths."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    n, H, W = 30000, 192, 256
+    sc, cam = _raw_scene("c2", n, H, W, S, rs, ex)
+    lv = {k: v.detach() for k, v in _leaves(sc, cam).items()}
+    rgb_a, alpha_a, depth_a, dim_a, reused_a, proj = _depth_chain(sc, cam, lv, reuse=True)
+    rgb_b, alpha_b, depth_b, dim_b, reused_b, _ = _depth_chain(sc, cam, lv, reuse=False)
+    assert reused_a == expect_reuse and not reused_b
+    assert torch.equal(dim_a, dim_b) and torch.equal(depth_a, depth_b) and torch.equal(rgb_a, rgb_b)
+    # oracle: static blend of the depths over the reference's full lists
+    c = lambda t: t.detach().cpu().numpy()
+    b = O.bin_and_sort(c(proj["xys"]), c(proj["depths"]), c(proj["radii"]), c(proj["nth"]), H, W, 16)
+    zero2 = np.zeros((n, 2), np.float32)
+    img, _, _ = O.rasterize_forward(H, W, 16, 1, b["gaussian_ids_sorted"], b["tile_bins"], c(proj["xys"]), zero2, 0.0, 0.0,
+                                    c(proj["conics"]), np.repeat(c(proj["depths"])[:, None], 3, 1).astype(np.float32), c(proj["opac"]),
+                                    np.zeros(3, np.float32))
+    diff = (dim_a[..., 0].cpu() - torch.from_numpy(img[..., 0])).abs() / max(1.0, float(dim_a.max()))
+    assert float((diff > 2e-5).float().mean()) <= 1e-3 and float(diff.max()) < 1e-2
+    # fused operator: same depth image from its own lists
+    from gsplat.fused import render_gaussians
+    with torch.no_grad():
+        rgb_f, alpha_f, info = render_gaussians(lv["means"], lv["log_scales"], lv["quats"], lv["opacity_logit"], lv["sh_dc"], lv["sh_rest"],
+                                                lv["viewmat"], cam["cam_pos"], lv["lin"], lv["ang"], cam["fx"], cam["fy"], cam["cx"],
+                                                cam["cy"], H, W, 16, lv["bg"], rolling_shutter_time=rs, exposure_time=ex,
+                                                blur_samples=S if ex > 0 else 1, sh_degree_to_use=3, return_depth=True)
+    assert info["depth"].shape == (H, W, 1) and "_lists" not in info
+    covered = alpha_a[..., 0] > 0.05
+    dd = (info["depth"][..., 0] - depth_a[..., 0]).abs()[covered] / depth_a[..., 0][covered].clamp_min(1e-3)
+    assert covered.any() and float((dd > 1e-3).float().mean()) <= 2e-3

@@ -89,3 +89,66 @@ def test_l1_loss_with_the_gamma_step_folded_in():
         assert float(g_out[lin.detach() > 1.0].abs().max()) == 0.0 and float(g_out.view(-1)[1].abs()) > 0.0
     with pytest.raises(ValueError):
         l1_loss(lin, target, gamma=0.0)
+
+
+@pytest.mark.parametrize("tag", ["rgb", "rgba"])
+def test_l1_on_the_uint8_dataset_image_vs_reference_golden(tag):
+    """b200_l1_loss_u8 against tests/golden/loss_target.npz -- get_gt_img / composite_with_background of the REFERENCE
+    model (imported by tests/golden/make_golden_loss.py) followed by its clamp / mask / L1 lines: prepared target bit
+    for bit, loss to 5e-7, cotangent w.r.t. the (linear) render to float rounding of pow."""
+    import os
+
+    import numpy as np
+
+    from gsplat.losses import l1_loss_and_grad
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_target.npz"))
+    img = torch.from_numpy(G[f"{tag}_image"]).cuda()
+    bg = torch.from_numpy(G[f"{tag}_background"]).cuda()
+    linear = torch.from_numpy(G[f"{tag}_linear"]).cuda()
+    mask = torch.from_numpy(G[f"{tag}_mask"]).cuda()
+    for level in (0, 12):
+        for use_mask in (0, 1):
+            for gm in (0, 1):
+                key = f"{tag}_l{level}_m{use_mask}_g{gm}"
+                loss, grad, target = l1_loss_and_grad(linear, img, 2.2 if gm else None, background=bg, min_rgb_level=float(level),
+                                                      mask=mask if use_mask else None, return_target=True)
+                assert torch.equal(target.cpu(), torch.from_numpy(G[key + "_target"])), key
+                assert abs(float(loss) - float(G[key + "_loss"])) < 5e-7, key
+                ref = torch.from_numpy(G[key + "_grad"])
+                # (sign flips where |pred - target| is a rounding error of pow: none on this fixture)
+                torch.testing.assert_close(grad.cpu(), ref, rtol=2e-5, atol=1e-9, msg=key)
+    # autograd form, and the trainer-facing photometric loss on the same uint8 image
+    p = linear.clone().requires_grad_(True)
+    out = l1_loss(p, img, 2.2, background=bg, min_rgb_level=12.0, mask=mask)
+    out.backward()
+    torch.testing.assert_close(p.grad.cpu(), torch.from_numpy(G[f"{tag}_l12_m1_g1_grad"]), rtol=2e-5, atol=1e-9)
+    pred = linear.clamp(max=1.0)
+    want = photometric_loss(pred, torch.from_numpy(G[f"{tag}_l12_m0_g0_target"]).cuda(), 0.2)
+    got = photometric_loss(pred, img, 0.2, background=bg, min_rgb_level=12.0)
+    assert torch.equal(want, got)
+    with pytest.raises(ValueError):
+        l1_loss(linear, torch.from_numpy(G[f"{tag}_l0_m0_g0_target"]).cuda(), mask=mask)  # options need the uint8 image
+    if tag == "rgba":
+        with pytest.raises(ValueError):
+            l1_loss(linear, img)  # RGBA without a background colour
+
+
+def test_pipelined_trainer_takes_the_uint8_image_without_a_conversion_pass():
+    """gsplat.dp hands the dataset's uint8 image to gsplat.losses.l1_loss as it is: same loss as the float image."""
+    import gsplat.synthetic as synthetic
+    from gsplat.dp import FlatGaussians, PipelinedTrainer
+
+    losses = []
+    for as_u8 in (False, True):
+        sc = synthetic.make_scene("c2", device="cuda", n_override=20000, n_cameras=1)
+        sc.update(H=128, W=160, fx=80.0, fy=80.0, cx=80.0, cy=64.0)
+        cam = sc["cameras"][0]
+        cam.update(fx=80.0, fy=80.0, cx=80.0, cy=64.0, vel0=torch.cat([cam["lin_vel"], cam["ang_vel"]]))
+        u8 = (torch.rand(128, 160, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 255).to(torch.uint8)
+        model = FlatGaussians(sc, "cuda", n_cameras=1, optimize_velocities=True)
+        tr = PipelinedTrainer(model, sc, use_graphs=False)
+        tr.prepare(cam, 0)
+        loss = tr.train_step(u8 if as_u8 else u8.float() / 255)
+        losses.append(float(loss))
+        tr.finish()
+    assert abs(losses[0] - losses[1]) < 1e-7, losses

@@ -294,3 +294,33 @@ def test_unmodified_splatfacto_eval_pass_renders_depth_through_this_package(spla
     covered = ref_alpha > 0.5
     d = _n(out["depth"][..., 0])
     assert covered.any() and np.all(d[covered] > 1.5) and np.all(d[covered] < 4.5)  # the cloud sits 2..4 units in front
+
+
+@pytest.mark.parametrize("rolling_shutter", [False, True])
+def test_eval_depth_pass_reuses_the_colour_pass_lists(splatfacto, oracle_C, monkeypatch, rolling_shutter):
+    """Eval with motion blur: the caller's second (static, depth-coloured) rasterize_gaussians call (splatfacto.py:881-897)
+    bins nothing when the colour pass had no rolling shutter and an odd sample count -- its lists contain the static
+    lists (gsplat/rasterize.py) -- and bins again when it had.  Same depth image either way."""
+    sf, Cameras, SceneBox = splatfacto
+    H, W, n = 32, 48, 300
+    model = _make_model(sf, SceneBox, n, training=False, velocity_opt=False)
+    meta = dict(exposure_time=1 / 60, cam_idx=0)
+    if rolling_shutter:
+        meta["rolling_shutter_time"] = 1 / 50
+    cam = Cameras(camera_to_worlds=torch.eye(4)[:3].unsqueeze(0).clone(), fx=W / 2.0, fy=W / 2.0, cx=W / 2.0, cy=H / 2.0, width=W,
+                  height=H, velocities=torch.tensor([[0.3, -0.2, 0.1, 0.05, 0.4, -0.3]]), metadata=meta)
+    with torch.no_grad():
+        out = model.get_outputs(cam)
+    blends = [c for c in oracle_C if c[0] == "blend_fwd"]
+    assert blends[0][1] == 5 and blends[1] == ("blend_fwd", 1, 0.0, 0.0)
+    assert len([c for c in oracle_C if c[0] == "bin"]) == (2 if rolling_shutter else 1)
+    del oracle_C[:]
+    monkeypatch.setenv("B200SPLAT_NO_LIST_REUSE", "1")
+    import gsplat.rasterize as R
+    R._last_lists.clear()
+    with torch.no_grad():
+        out2 = model.get_outputs(cam)
+    assert len([c for c in oracle_C if c[0] == "bin"]) == 2
+    assert torch.equal(out["depth"], out2["depth"]) and torch.equal(out["rgb"], out2["rgb"])
+    d = out["depth"][..., 0][out["accumulation"][..., 0] > 0.5]  # (blurred coverage can exceed the static one at the rim: depth 0 there)
+    assert d.numel() > 0 and float(d.min()) > 1.0 and float(d.max()) < 4.5
