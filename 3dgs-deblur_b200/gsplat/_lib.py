@@ -155,7 +155,7 @@ SYNC_CHECKS = os.environ.get("B200SPLAT_SYNC_CHECKS", "0") == "1"
 _pending_flags = {}   # device index -> int32 device tensor awaiting a read-back
 _quat_flags = {}      # device index -> the device's persistent (sticky) flag word: zero unless a check has failed
 _host_scratch_np = {}
-_host_scratch = {}    # device index -> pinned int32[8]: [0] total, [1] flag (scan path); [0:4] totals, [4] flag (cull path)
+_host_scratch = {}    # (device index, stream) -> pinned int32[8]: [0] total, [1] flag (scan path); [0:4] totals, [4] flag (cull path)
 
 
 def new_quat_flag(device):
@@ -172,20 +172,28 @@ def take_pending_flag(device):
     return _pending_flags.pop(device.index, None)
 
 
+def _scratch_key(device):
+    # one pinned block per (device, stream): two streams (or threads on their own streams) reading totals back at the same
+    # time must not share the words their copies land in
+    return (device.index, torch.cuda.current_stream(device).cuda_stream)
+
+
 def host_scratch(device):
-    buf = _host_scratch.get(device.index)
+    key = _scratch_key(device)
+    buf = _host_scratch.get(key)
     if buf is None:
         buf = torch.zeros(8, dtype=torch.int32).pin_memory()
-        _host_scratch[device.index] = buf
-        _host_scratch_np[device.index] = (buf.data_ptr(), buf.numpy())
+        _host_scratch[key] = buf
+        _host_scratch_np[key] = (buf.data_ptr(), buf.numpy())
     return buf
 
 
 def host_scratch_np(device):
     """(address, numpy view) of the pinned scratch: reads after the host sync cost ~0.1 us instead of a tensor index."""
-    if device.index not in _host_scratch_np:
+    key = _scratch_key(device)
+    if key not in _host_scratch_np:
         host_scratch(device)
-    return _host_scratch_np[device.index]
+    return _host_scratch_np[key]
 
 
 def raise_if_flagged(flag_value):
