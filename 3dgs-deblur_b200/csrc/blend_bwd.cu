@@ -284,6 +284,10 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
 #ifndef B200_BWD_SMEM_REDUCE
 #define B200_BWD_SMEM_REDUCE 1
 #endif
+// B200_BWD_T_SELECT=0: drop the two selects that keep a masked pixel's transmittance (A/B build; relies on rcp.approx(1) == 1)
+#ifndef B200_BWD_T_SELECT
+#define B200_BWD_T_SELECT 1
+#endif
 constexpr int RED_VALUES = 13;  // rgb 3, conic 3, xy 2, |xy| 2, pixel velocity 2, opacity 1
 constexpr int RED_STRIDE = 36;  // floats per row: 32 lanes + 4 of padding (rows stay 16-byte aligned, halves hit distinct banks)
 #ifndef B200_BWD_MIN_CTAS
@@ -444,7 +448,9 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                     const f2 zero = f2_splat(0.f);
                     f2 sxx = zero, sxy = zero, syy = zero, gxs = zero, gys = zero, pvx = zero, pvy = zero, vop = zero, facsum = zero;
                     float gxa = 0.f, gya = 0.f;
+#if B200_SAMPLE_VOTE
                     bool any = false;
+#endif
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         if (!(smask & (1u << s)) || idx > smax[s]) continue;  // warp-uniform
@@ -457,13 +463,18 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                         bool ok1 = (idx <= bin_final[1][s]) && !(sg1 > cut || sg1 < 0.f);
                         if (inside[0]) B200_COUNT(3, 1);
                         if (inside[1]) B200_COUNT(3, 1);
-                        // exp(-sigma): masked pixels evaluate exp(0)
-                        float v0 = exp_neg_approx(ok0 ? sg0 : 0.f), v1 = exp_neg_approx(ok1 ? sg1 : 0.f);
+                        // exp(-sigma) = 2^(-sigma log2 e) (exp_neg_approx's own form, the product packed): masked pixels evaluate 2^0
+                        const f2 ex = f2_mul(sigma, f2_splat(-1.4426950408889634f));
+                        float v0, v1;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v0) : "f"(ok0 ? f2_lo(ex) : 0.f));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v1) : "f"(ok1 ? f2_hi(ex) : 0.f));
                         float a0 = fminf(0.99f, Bq.w * v0), a1 = fminf(0.99f, Bq.w * v1);
                         ok0 = ok0 && !(a0 < 1.f / 255.f);
                         ok1 = ok1 && !(a1 < 1.f / 255.f);
+#if B200_SAMPLE_VOTE
                         if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
                         any = true;
+#endif
                         if (ok0) B200_COUNT(4, 1);
                         if (ok1) B200_COUNT(4, 1);
                         // masked pixels: vis = alpha = 0  =>  ra = 1, fac = 0, v_sigma = 0, every accumulated term exactly 0
@@ -477,7 +488,11 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                         const f2 v_alpha = f2_fma(Tn, cdot, f2_mul(ra, D[s]));  // backward.cu:303-311
                         // no zeroing when the clamp is active (backward.cu:317)
                         const f2 v_sigma = f2_mul(f2_sub(zero, ov), v_alpha);
+#if B200_BWD_T_SELECT
                         Tm[s] = f2_make(ok0 ? f2_lo(Tn) : f2_lo(Tm[s]), ok1 ? f2_hi(Tn) : f2_hi(Tm[s]));
+#else
+                        Tm[s] = Tn;  // masked pixels: alpha = 0, ra = rcp(1) = 1 exactly (tools/micro/rcp_check.cu), Tn == Tm bit for bit
+#endif
                         D[s] = f2_fma(f2_sub(zero, fac), cdot, D[s]);     // running buffer, :313-315
                         facsum = f2_add(facsum, fac);
                         const f2 u = f2_mul(v_sigma, dx), w = f2_mul(v_sigma, dy);
@@ -490,7 +505,11 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                         pvx = f2_fma(gx, tau, pvx); pvy = f2_fma(gy, tau, pvy);
                         vop = f2_fma(vis, v_alpha, vop);
                     }
+#if B200_SAMPLE_VOTE
                     if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
+#endif
+                    // (without the votes a visit whose every pixel failed the alpha test reduces 13 exact zeros and the
+                    // `tot != 0` guard below drops the atomics: same memory effect as the reference's skip)
                     if (lane == 0) B200_COUNT(5, 1);
 #if B200_BWD_SMEM_REDUCE
                     // lane l parks value j at row j, column l (bank 4 j + l: conflict free); lanes 2 j and 2 j + 1 then add up

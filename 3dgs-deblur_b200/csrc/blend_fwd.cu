@@ -314,6 +314,9 @@ __global__ void __launch_bounds__(128, B200_FWD_MIN_CTAS) blend_forward_kernel2(
                 const unsigned my_mask = (e < cnt) ? sample_mask_exact<S>(s_rec[st][e], win, p.g.exposure) : 0u;
                 unsigned m = __ballot_sync(0xffffffffu, my_mask != 0u);
                 if (e < cnt) B200_COUNT(0, 1);
+#if B200_FWD_ALIVE_PER_CHUNK
+                const unsigned alive_chunk = alive[0] + alive[1];  // (bits only ever clear: the sum drops iff one did)
+#endif
                 while (m) {
                     const int src = __ffs(m) - 1;
                     const int k = c0 + src;
@@ -330,7 +333,9 @@ __global__ void __launch_bounds__(128, B200_FWD_MIN_CTAS) blend_forward_kernel2(
                     const f2 CR = f2_splat(C.x * inv_s), CG = f2_splat(C.y * inv_s), CBl = f2_splat(C.z * inv_s);
                     const f2 dx0 = f2_sub(f2_splat(A.x), PX), dy0 = f2_sub(f2_splat(A.y), PY);
                     const int idx = start + k;
+#if !B200_FWD_ALIVE_PER_CHUNK
                     const unsigned alive_before = alive[0] + alive[1];
+#endif
 #ifdef B200_BLEND_COUNTERS
                     bool blended_ = false;
 #endif
@@ -355,7 +360,9 @@ __global__ void __launch_bounds__(128, B200_FWD_MIN_CTAS) blend_forward_kernel2(
                         const float a0 = fminf(0.999f, f2_lo(ov)), a1 = fminf(0.999f, f2_hi(ov));
                         ok0 = ok0 && !(a0 < 1.f / 255.f);
                         ok1 = ok1 && !(a1 < 1.f / 255.f);
+#if B200_SAMPLE_VOTE
                         if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+#endif
                         if (ok0) B200_COUNT(4, 1);
                         if (ok1) B200_COUNT(4, 1);
 #ifdef B200_BLEND_COUNTERS
@@ -377,12 +384,23 @@ __global__ void __launch_bounds__(128, B200_FWD_MIN_CTAS) blend_forward_kernel2(
 #ifdef B200_BLEND_COUNTERS
                     if (__any_sync(0xffffffffu, blended_) && lane == 0) B200_COUNT(5, 1);
 #endif
+#if !B200_FWD_ALIVE_PER_CHUNK
                     // (bits only ever clear, so the sum of the two masks drops iff one did)
                     if (__any_sync(0xffffffffu, (alive[0] + alive[1]) != alive_before)) {  // rare: refresh the warp's live set
                         walive = __reduce_or_sync(0xffffffffu, alive[0] | alive[1]);
                         if (walive == 0u) { m = 0; c0 = cnt; }
                     }
+#endif
                 }
+#if B200_FWD_ALIVE_PER_CHUNK
+                // the warp's live-sample set is refreshed once per 32 entries instead of after every visit (a vote + compare
+                // per visit for an event that happens S times per pixel): until then a sample that just finished for every
+                // lane is still entered, fully masked -- no effect on any output
+                if (__any_sync(0xffffffffu, (alive[0] + alive[1]) != alive_chunk)) {
+                    walive = __reduce_or_sync(0xffffffffu, alive[0] | alive[1]);
+                    if (walive == 0u) c0 = cnt;
+                }
+#endif
             }
         }
         // all warps are done with stage `st` (it is refilled two batches from now) + early exit vote
