@@ -270,6 +270,31 @@ __device__ __forceinline__ bool tile_survives(const PackedGaussian &g, int tx, i
     return may_touch_rect_closed_form(g, x0, x1, y0, y1, r0, r1, c.exposure, c.S);
 }
 
+// Depth-sort keys of the culled binning: the depth bits of every Gaussian that reserves at least one real tile slot (the
+// same `emitted_ref > 0` as cull_prep_kernel), 0xffffffff for the rest.  Its own tiny kernel so that the depth sort -- the
+// longest chain of the binning (histogram + 4 onesweep passes) -- can start on the side stream BEFORE cull_prep / scan /
+// count instead of after cull_prep (B200_CULL_EARLY_SORT=0: keys written by cull_prep_kernel, sort forked after it).
+#ifndef B200_CULL_EARLY_SORT
+#define B200_CULL_EARLY_SORT 1
+#endif
+__global__ void __launch_bounds__(256) cull_keys_kernel(int n, const PackedGaussian *__restrict__ rec,
+                                                        const float *__restrict__ depths, const int32_t *__restrict__ radii,
+                                                        const int32_t *__restrict__ tiles_hit, int tbx, int tby, int bw,
+                                                        uint32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int r = radii[g], reserved = tiles_hit[g];
+    int emitted_ref = 0;
+    if (r > 0 && reserved > 0) {
+        const float2 xy = *reinterpret_cast<const float2 *>(&rec[g].x);
+        int x0, y0, x1, y1;
+        tile_bbox(xy.x, xy.y, (float)r, tbx, tby, (float)bw, x0, y0, x1, y1);
+        emitted_ref = min(max(0, (x1 - x0) * (y1 - y0)), reserved);
+    }
+    keys[g] = emitted_ref > 0 ? (uint32_t)__float_as_int(depths[g]) : 0xffffffffu;
+    vals[g] = g;
+}
+
 // counters: [0] = sum of reserved slots (the reference's num_intersects), [1] = phantom slots,
 //           [2] = 1 if Gaussian 0 can touch tile 0, [3] = number of list entries after culling (filled later),
 // Work is split into chunks of 32 candidate tiles (a screen-filling splat reserves 2500 of them, most reserve < 16):
@@ -300,8 +325,10 @@ __global__ void __launch_bounds__(256) cull_prep_kernel(int n, const PackedGauss
         chunks[g] = (emitted_ref + 31) >> 5;
         survivors[g] = 0;
         cursor[g] = 0;
+#if !B200_CULL_EARLY_SORT
         keys[g] = emitted_ref > 0 ? (uint32_t)__float_as_int(depths[g]) : 0xffffffffu;
         vals[g] = g;
+#endif
         phantom = max(0, reserved - emitted_ref);
         if (g == 0) counters[2] = (c.per_sample ? tile_survives<true>(rec[0], 0, 0, c) : tile_survives<false>(rec[0], 0, 0, c)) ? 1 : 0;
     }
@@ -744,9 +771,25 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
     SideStream side;
     B200_REQUIRE(side_stream(side), "could not create the binning side stream");
     B200_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+#if B200_CULL_EARLY_SORT
+    // the depth sort only needs depths and the visibility of each Gaussian: it is forked first and runs beside cull_prep,
+    // the scan and the tile tests (chains of short kernels, the sort's being the longest)
+    {
+        std::lock_guard<std::mutex> lock(side_mu);
+        B200_CUDA(cudaEventRecord(side.fork, st));
+        B200_CUDA(cudaStreamWaitEvent(side.stream, side.fork, 0));
+        cull_keys_kernel<<<ceil_div(n, 256), 256, 0, side.stream>>>(n, rec, depths, radii, num_tiles_hit, c.tbx, c.tby, c.bw, keys_a,
+                                                                    vals_a);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, order, n, 0, 32, side.stream));
+        count_launch(5);
+        B200_CUDA(cudaEventRecord(side.join, side.stream));
+    }
+#endif
     cull_prep_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, rec, depths, radii, num_tiles_hit, c, keys_a, vals_a, bbox, chunks,
                                                        survivors, cursor, counters);
     B200_LAUNCH_CHECK();
+#if !B200_CULL_EARLY_SORT
     // the depth sort only needs the keys: it runs beside the scan + tile tests, both are chains of short kernels
     {
         std::lock_guard<std::mutex> lock(side_mu);
@@ -756,6 +799,7 @@ extern "C" int b200_bin_cull_count(int num_points, const void *packed, const flo
         count_launch(5);
         B200_CUDA(cudaEventRecord(side.join, side.stream));
     }
+#endif
     B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, chunks, chunk_off, n, st));
     count_launch(2);
     (c.per_sample ? cull_chunks_kernel<false, true> : cull_chunks_kernel<false, false>)<<<CULL_COUNT_GRID, 256, 0, st>>>(

@@ -284,16 +284,17 @@ __global__ void __launch_bounds__(BLEND_THREADS / PPL, PPL == 2 ? 5 : (PPL == 4 
 #ifndef B200_BWD_SMEM_REDUCE
 #define B200_BWD_SMEM_REDUCE 1
 #endif
-// B200_BWD_T_SELECT=0: drop the two selects that keep a masked pixel's transmittance (A/B build; relies on rcp.approx(1) == 1)
+// B200_BWD_T_SELECT=1 (A/B build): keep a masked pixel's transmittance with two selects instead of relying on
+// rcp.approx(1) == 1 (true on sm_100a: tools/micro/rcp_check.cu; c2 backward 617 -> 610 us without them)
 #ifndef B200_BWD_T_SELECT
-#define B200_BWD_T_SELECT 1
+#define B200_BWD_T_SELECT 0
 #endif
 constexpr int RED_VALUES = 13;  // rgb 3, conic 3, xy 2, |xy| 2, pixel velocity 2, opacity 1
 constexpr int RED_STRIDE = 36;  // floats per row: 32 lanes + 4 of padding (rows stay 16-byte aligned, halves hit distinct banks)
 #ifndef B200_BWD_MIN_CTAS
 #define B200_BWD_MIN_CTAS 5  // 96 registers; A/B of 4 / 6 in DESIGN.md section 9
 #endif
-template <int S>
+template <int S, bool VOTE>
 __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2(const BlendBwdParams p) {
     constexpr int NT = 128;
     __shared__ __align__(128) PackedGaussian s_rec[BLEND_STAGES][BLEND_BATCH];
@@ -448,9 +449,7 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                     const f2 zero = f2_splat(0.f);
                     f2 sxx = zero, sxy = zero, syy = zero, gxs = zero, gys = zero, pvx = zero, pvy = zero, vop = zero, facsum = zero;
                     float gxa = 0.f, gya = 0.f;
-#if B200_SAMPLE_VOTE
                     bool any = false;
-#endif
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         if (!(smask & (1u << s)) || idx > smax[s]) continue;  // warp-uniform
@@ -471,10 +470,10 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                         float a0 = fminf(0.99f, Bq.w * v0), a1 = fminf(0.99f, Bq.w * v1);
                         ok0 = ok0 && !(a0 < 1.f / 255.f);
                         ok1 = ok1 && !(a1 < 1.f / 255.f);
-#if B200_SAMPLE_VOTE
-                        if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
-                        any = true;
-#endif
+                        if (VOTE) {
+                            if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+                            any = true;
+                        }
                         if (ok0) B200_COUNT(4, 1);
                         if (ok1) B200_COUNT(4, 1);
                         // masked pixels: vis = alpha = 0  =>  ra = 1, fac = 0, v_sigma = 0, every accumulated term exactly 0
@@ -505,9 +504,7 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                         pvx = f2_fma(gx, tau, pvx); pvy = f2_fma(gy, tau, pvy);
                         vop = f2_fma(vis, v_alpha, vop);
                     }
-#if B200_SAMPLE_VOTE
-                    if (!__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
-#endif
+                    if (VOTE && !__any_sync(0xffffffffu, any)) continue;  // backward.cu:281-283
                     // (without the votes a visit whose every pixel failed the alpha test reduces 13 exact zeros and the
                     // `tot != 0` guard below drops the atomics: same memory effect as the reference's skip)
                     if (lane == 0) B200_COUNT(5, 1);
@@ -560,8 +557,16 @@ template <int S>
 static int launch_bwd(const BlendBwdParams &p, cudaStream_t st) {
     if (p.g.bw == 16 && blend_pixels_per_lane(true) == 4)  // experimental (B200_BLEND_PPL_BWD=4)
         blend_backward_kernel<S, 4><<<p.g.tbx * p.g.tby, BLEND_THREADS / 4, 0, st>>>(p);
-    else if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2 && blend_packed())
-        blend_backward_kernel2<S><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
+    else if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2 && blend_packed()) {
+        // per-sample votes ("does any lane hold a contributing pixel", then skip the gradient algebra): without rolling
+        // shutter the exact cull leaves 4 % of the entered sample blocks empty and the vote + branch costs more than the
+        // masked arithmetic (c2: 646 -> 617 us); with it the warp's time window widens the cull and the skip pays (c4:
+        // 4988 us with, 5573 without) -- profiles/r2x_blend_ab.txt
+        if (B200_SAMPLE_VOTE || p.g.rs_time != 0.f)
+            blend_backward_kernel2<S, true><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
+        else
+            blend_backward_kernel2<S, false><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
+    }
     else if (p.g.bw == 16 && blend_pixels_per_lane(true) == 2)  // B200_BLEND_PACKED=0: the scalar two-pixel kernel (A/B)
         blend_backward_kernel<S, 2><<<p.g.tbx * p.g.tby, BLEND_THREADS / 2, 0, st>>>(p);
     else

@@ -38,9 +38,11 @@ extern __device__ unsigned long long g_blend_counters[16];
 #define B200_COUNT_FLUSH(base) ((void)0)
 #endif
 
-// Per-sample "does any lane of the warp hold a contributing pixel" votes in the packed kernels: with the exact cull in
-// front, 96 % of the sample blocks a warp enters do (ncu r2w: backward 692 k of 720 k, forward 696 k of 727 k), so the
-// vote + branch costs more than the masked arithmetic it skips.  -DB200_SAMPLE_VOTE=1 restores them (A/B build).
+// Per-sample "does any lane of the warp hold a contributing pixel" votes in the packed kernels.  With the exact cull in
+// front, 96 % of the sample blocks a warp enters do at config 2 (ncu r2w: backward 692 k of 720 k, forward 696 k of 727 k),
+// so the vote + branch costs more than the masked arithmetic it skips: the forward never votes (c2 333 -> 314 us, c4 2429 ->
+// 2367), the backward votes only with rolling shutter (blend_bwd.cu: launch_bwd).  -DB200_SAMPLE_VOTE=1 restores the votes
+// everywhere (A/B build).
 #ifndef B200_SAMPLE_VOTE
 #define B200_SAMPLE_VOTE 0
 #endif

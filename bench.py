@@ -125,6 +125,7 @@ def cpu_step_factory(cfg, n_override=None):
     import numpy as np
     import torch
 
+    _forget_flat_oracle()
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import oracle as O
     from util_scene import scene_np
@@ -190,6 +191,7 @@ def run_cpu_arm(args, one_shot=False):
     # OpenMP runtime reads the variable when liboracle.so is loaded (below), so override it here
     os.environ["OMP_NUM_THREADS"] = str(cores)
     step, d = cpu_step_factory(args.config, args.n)
+    _forget_flat_oracle()
     from oracle import oracle as _O
     cores = _O.set_threads(cores)  # the count the OpenMP runtime actually uses
     H = d["H"]
@@ -291,22 +293,40 @@ def make_cameras(scene, device, optimize_vel):
     return cams
 
 
-def measure_ref_gpu(args, scene_dev, cams, targets, n_img, value, loss_fn, dev):
-    """`ref_gpu`: train-step images/s of the UNMODIFIED reference gsplat CUDA kernels (oracle/_ref) on this arm's
-    workload, three ways, plus this repo on the zero-motion variant so the ratio without the reference's phantom-tile-0
-    tail is visible.  Reported beside the arm's value; never part of a timed region of the arm."""
-    import torch
+def _forget_flat_oracle():
+    """Take oracle/ off sys.path (every occurrence) and drop a top-level module `oracle` that is oracle/oracle.py rather
+    than the package: with the directory on the path `from oracle import oracle` finds the FILE first."""
+    odir = os.path.realpath(os.path.join(ROOT, "oracle"))
+    sys.path[:] = [p for p in sys.path if os.path.realpath(p or ".") != odir]
+    m = sys.modules.get("oracle")
+    if m is not None and not hasattr(m, "__path__"):
+        del sys.modules["oracle"]
 
-    # (oracle/ holds both the package `oracle` and flat helper modules: put the directory on the path only while the
-    # helpers are imported, or a later `from oracle import oracle` would find oracle/oracle.py first)
+
+def import_oracle_helpers():
+    """oracle/ holds both the package `oracle` and flat helper modules that import each other by bare name (and put their
+    own directory on sys.path to do so): the directory is on the path only while they are imported.  Round 2 shipped this
+    with a single `sys.path.remove`, the helpers' own insert survived it and the CPU baseline of the same process then
+    failed to import the package (r2u / r2y bench lines: cpu_baseline None)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     try:
         import build_ref
         import ref_bench
         import ref_ops  # noqa: F401
         import torch_oracle  # noqa: F401
-        sys.path.remove(os.path.join(ROOT, "oracle"))
-        sys.modules.pop("oracle", None) if not hasattr(sys.modules.get("oracle"), "__path__") else None
+    finally:
+        _forget_flat_oracle()
+    return build_ref, ref_bench
+
+
+def measure_ref_gpu(args, scene_dev, cams, targets, n_img, value, loss_fn, dev):
+    """`ref_gpu`: train-step images/s of the UNMODIFIED reference gsplat CUDA kernels (oracle/_ref) on this arm's
+    workload, three ways, plus this repo on the zero-motion variant so the ratio without the reference's phantom-tile-0
+    tail is visible.  Reported beside the arm's value; never part of a timed region of the arm."""
+    import torch
+
+    try:
+        build_ref, ref_bench = import_oracle_helpers()
 
         if not os.path.exists(build_ref.so_path()):
             return {"unavailable": "oracle/_ref/gsplat_ref_csrc.so not built (needs /root/reference at build time)"}

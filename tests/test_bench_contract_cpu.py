@@ -41,3 +41,17 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_is_silent_on_other_ranks():
     out = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert out.strip() == ""
+
+
+def test_cpu_baseline_imports_survive_the_reference_gpu_helpers():
+    """bench.py's default run measures `ref_gpu` (flat helper modules under oracle/, which put that directory on
+    sys.path) and then `cpu_baseline` (the package `oracle`) in ONE process: the second import must still find the
+    package.  (Rounds-2 bench lines r2u / r2y carried cpu_baseline None because it did not.)"""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.argv=['bench.py']; import bench; bench.import_oracle_helpers(); "
+            "step, d = bench.cpu_step_factory('c1'); from oracle import oracle as O; "
+            "assert hasattr(sys.modules['oracle'], '__path__'); print('ok', O.__name__)")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok oracle.oracle" in r.stdout, r.stderr[-800:]
