@@ -39,8 +39,10 @@ def _prepare(xys, colors, background, block_width):
 _last_lists = {}  # device index -> dict(tensors=..., geom=..., blur=..., n_isect, ids, bins)
 
 
-def _same_tensor(a, b):
-    return a.data_ptr() == b.data_ptr() and a._version == b._version and a.shape == b.shape and a.dtype == b.dtype
+def _same_tensor(a, b, version):
+    # b is the remembered alias of the tensor seen last time (it shares a's version counter if it is the same tensor, so
+    # the counter's VALUE at that time is remembered separately: an in-place write since then invalidates the lists)
+    return a.data_ptr() == b.data_ptr() and a._version == version and a.shape == b.shape and a.dtype == b.dtype
 
 
 def _remember_lists(per_gaussian, geom, blur, n_isect, ids, bins):
@@ -49,7 +51,8 @@ def _remember_lists(per_gaussian, geom, blur, n_isect, ids, bins):
         return
     # detached aliases keep the storages alive (an address can then not be handed to another tensor) without holding
     # the autograd graph; the version counter is shared with the caller's tensor
-    _last_lists[per_gaussian[0].device.index] = dict(tensors=[t.detach() for t in per_gaussian], geom=geom, blur=blur,
+    _last_lists[per_gaussian[0].device.index] = dict(tensors=[t.detach() for t in per_gaussian],
+                                                     versions=[t._version for t in per_gaussian], geom=geom, blur=blur,
                                                      n_isect=n_isect, ids=ids, bins=bins)
 
 
@@ -61,7 +64,7 @@ def _reusable_lists(per_gaussian, geom, n_samples, rs, ex):
     S0, rs0, ex0 = c["blur"]
     if rs0 != 0 or not (ex0 == 0 or S0 % 2 == 1):
         return None
-    if not all(_same_tensor(a, b) for a, b in zip(per_gaussian, c["tensors"])):
+    if not all(_same_tensor(a, b, v) for a, b, v in zip(per_gaussian, c["tensors"], c["versions"])):
         return None
     return c["n_isect"], c["ids"], c["bins"]
 

@@ -226,3 +226,63 @@ def test_fakes_have_the_real_wrappers_arity():
     bwd = inspect.signature(_C.project_gaussians_backward).parameters
     assert list(fwd)[:18][-1] == "clip_thresh" and "_vel_tensors" in fwd and "_quat_flag" in fwd
     assert all(k in bwd for k in ("_vel_tensors", "_exact", "_want_vel", "_want_viewmat", "_want_cov"))
+
+
+def test_static_second_pass_reuses_lists_only_when_they_provably_cover_it(fake_C):
+    """gsplat.rasterize list reuse (the caller's depth pass, splatfacto.py:881-897): same per-Gaussian tensors, static
+    second call, colour pass without rolling shutter and with an odd sample count (or no exposure)."""
+    import gsplat.rasterize as R
+    from gsplat.rasterize import rasterize_gaussians
+
+    def bins():
+        return [c for c in fake_C if isinstance(c, tuple) and c[0] == "bin_cull"]
+
+    def run(S, rs, ex, same=True, touch=False):
+        R._last_lists.clear()
+        del fake_C[:]
+        xys, depths, pv, radii, conics, nth, colors, opacity = _inputs()
+        rasterize_gaussians(xys, depths, pv, radii, conics, nth, colors, opacity, 20, 36, 16, None, True, rs, ex, S)
+        if touch:
+            with torch.no_grad():
+                conics.add_(0.0)  # an in-place write bumps the version counter: the lists may be stale
+        if not same:
+            conics = conics.clone()
+        depth_cols = depths[:, None].repeat(1, 3)
+        rasterize_gaussians(xys, depths, pv, radii, conics, nth, depth_cols, opacity, 20, 36, 16, background=torch.zeros(3))
+        return len(bins())
+
+    assert run(5, 0.0, 0.016) == 1          # odd sample count, no rolling shutter: reused
+    assert run(1, 0.0, 0.0) == 1            # static colour pass: reused
+    assert run(5, 0.0, 0.0) == 1            # no exposure: every sample sits at offset 0
+    assert run(4, 0.0, 0.016) == 2          # even count: no sample at offset 0
+    assert run(5, 0.02, 0.016) == 2         # rolling shutter: per-row offsets
+    assert run(5, 0.0, 0.016, same=False) == 2   # another tensor
+    assert run(5, 0.0, 0.016, touch=True) == 2   # same tensor, written since
+    # a second call that is not static never reuses
+    R._last_lists.clear()
+    del fake_C[:]
+    a = _inputs()
+    rasterize_gaussians(*a, 20, 36, 16, None, True, 0.0, 0.016, 5)
+    rasterize_gaussians(*a, 20, 36, 16, None, True, 0.0, 0.016, 5)
+    assert len(bins()) == 2
+
+
+def test_loss_target_options_are_checked_before_any_kernel():
+    from gsplat.losses import _target_options
+
+    pred = torch.zeros(16, 20, 3)
+    rgb, rgba = torch.zeros(16, 20, 3, dtype=torch.uint8), torch.zeros(16, 20, 4, dtype=torch.uint8)
+    ch, bg, level, mask = _target_options("l1_loss", pred, rgb, torch.ones(3), 12.0, torch.ones(16, 20, 1, dtype=torch.bool))
+    assert ch == 3 and bg is None and abs(level - 12.0 / 255.0) < 1e-12 and mask.shape == (16, 20) and mask.dtype == torch.float32
+    ch, bg, level, mask = _target_options("l1_loss", pred, rgba, torch.tensor([[0.1, 0.2, 0.3]]), 0.0, None)
+    assert ch == 4 and bg.shape == (3,) and level == 0.0 and mask is None
+    with pytest.raises(ValueError):
+        _target_options("l1_loss", pred, rgba, None, 0.0, None)            # RGBA needs a background
+    with pytest.raises(ValueError):
+        _target_options("l1_loss", pred, torch.zeros(16, 21, 3, dtype=torch.uint8), None, 0.0, None)
+    with pytest.raises(ValueError):
+        _target_options("l1_loss", pred, rgb, None, 0.0, torch.ones(16, 21))  # mask of another size
+    with pytest.raises(ValueError):
+        _target_options("l1_loss", pred, rgb, None, -1.0, None)
+    with pytest.raises(ValueError):
+        _target_options("l1_loss", pred, rgba, torch.ones(4), 0.0, None)
