@@ -443,10 +443,11 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                     const float cut = C.w + 1e-4f;
                     const f2 VX = f2_splat(A.z), VY = f2_splat(A.w);
                     const f2 CA = f2_splat(Bq.x), CB = f2_splat(Bq.y), CC = f2_splat(Bq.z);
-                    const f2 HA = f2_splat(0.5f * Bq.x), HC = f2_splat(0.5f * Bq.z), OP = f2_splat(Bq.w);
+                    const f2 HA = f2_splat(0.5f * Bq.x), HC = f2_splat(0.5f * Bq.z), NOP = f2_splat(-Bq.w);
                     const f2 dx0 = f2_sub(f2_splat(A.x), PX), dy0 = f2_sub(f2_splat(A.y), PY);
                     const f2 cdot = f2_fma(f2_splat(C.x), VO0, f2_fma(f2_splat(C.y), VO1, f2_mul(f2_splat(C.z), VO2)));
                     const f2 zero = f2_splat(0.f);
+                    const f2 ncdot = f2_sub(zero, cdot);  // (negations hoisted out of the sample blocks: exact)
                     f2 sxx = zero, sxy = zero, syy = zero, gxs = zero, gys = zero, pvx = zero, pvy = zero, vop = zero, facsum = zero;
                     float gxa = 0.f, gya = 0.f;
                     bool any = false;
@@ -479,20 +480,20 @@ __global__ void __launch_bounds__(128, B200_BWD_MIN_CTAS) blend_backward_kernel2
                         // masked pixels: vis = alpha = 0  =>  ra = 1, fac = 0, v_sigma = 0, every accumulated term exactly 0
                         const f2 vis = f2_make(ok0 ? v0 : 0.f, ok1 ? v1 : 0.f);
                         const f2 alpha = f2_make(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
-                        const f2 ov = f2_mul(OP, vis);
+                        const f2 nov = f2_mul(NOP, vis);  // -opacity * exp(-sigma)
                         const f2 om = f2_sub(f2_splat(1.f), alpha);
                         const f2 ra = f2_make(rcp_approx(f2_lo(om)), rcp_approx(f2_hi(om)));
                         const f2 Tn = f2_mul(Tm[s], ra);                 // T / S of backward.cu:294-296
                         const f2 fac = f2_mul(alpha, Tn);
                         const f2 v_alpha = f2_fma(Tn, cdot, f2_mul(ra, D[s]));  // backward.cu:303-311
                         // no zeroing when the clamp is active (backward.cu:317)
-                        const f2 v_sigma = f2_mul(f2_sub(zero, ov), v_alpha);
+                        const f2 v_sigma = f2_mul(nov, v_alpha);
 #if B200_BWD_T_SELECT
                         Tm[s] = f2_make(ok0 ? f2_lo(Tn) : f2_lo(Tm[s]), ok1 ? f2_hi(Tn) : f2_hi(Tm[s]));
 #else
                         Tm[s] = Tn;  // masked pixels: alpha = 0, ra = rcp(1) = 1 exactly (tools/micro/rcp_check.cu), Tn == Tm bit for bit
 #endif
-                        D[s] = f2_fma(f2_sub(zero, fac), cdot, D[s]);     // running buffer, :313-315
+                        D[s] = f2_fma(fac, ncdot, D[s]);                  // running buffer, :313-315
                         facsum = f2_add(facsum, fac);
                         const f2 u = f2_mul(v_sigma, dx), w = f2_mul(v_sigma, dy);
                         sxx = f2_fma(u, dx, sxx); sxy = f2_fma(u, dy, sxy); syy = f2_fma(w, dy, syy);

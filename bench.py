@@ -602,7 +602,7 @@ def run_gpu_arm(args):
 
     # ---- end to end: host buffers in, loss out, every step (pinned uint8 image + camera H2D, loss D2H)
     cam_host = [torch.cat([c["viewmat"].reshape(-1), c["lin_vel"], c["ang_vel"], c["cam_pos"]]).pin_memory() for c in my]
-    e2e_steps = max(5, args.steps // 2)
+    e2e_steps = max(20, args.steps)  # (wall-clock timed: enough steps that filling the prefetch pipeline is noise)
 
     # double-buffered prefetch on a copy stream (gsplat.data.ImagePrefetcher: what a datamanager does -- pinned uint8
     # image + camera floats), the loss of step k-1 is read back while step k is already queued; every step's inputs cross
@@ -656,8 +656,9 @@ def run_gpu_arm(args):
     h2d = prefetcher.bytes_per_step
     e2e = {"value": world * 1000.0 / e2e_ms, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4 + 8, "steps": e2e_steps,
-           "path": "gsplat.project_gaussians / spherical_harmonics / rasterize_gaussians via gsplat.dp." + (
-               "PipelinedTrainer" if pipelined else "ImageShardedTrainer")}
+           "path": (_api(args.operators) if pipelined else _api("dropin")) + " via gsplat.dp." + (
+               "PipelinedTrainer" if pipelined else "ImageShardedTrainer") + "; uint8 image + camera row from pinned host memory "
+                   "every step (gsplat.data.ImagePrefetcher), loss read back every step"}
     trainer_status = None
     if pipelined:
         trainer.finish()
