@@ -859,6 +859,23 @@ class PipelinedTrainer:
             with torch.cuda.stream(self.main):
                 m.rebind_leaves()
 
+    def reserve(self, entries: int):
+        """Make the tile lists hold at least `entries` (+ 30 % headroom) from now on.  A caller that knows its images' entry
+        counts (a measuring pass, a previous epoch) calls this once -- on every rank with the SAME number -- so that the
+        lists never grow mid-training: a growth means new CUDA graphs (two eager steps, then ~10 ms of capture), and in a
+        synchronous data-parallel step one rank's capture stalls all of them."""
+        want = self._round_capacity(int(1.3 * int(entries)) + 65536)
+        if self.capacity is None or want > self.capacity:
+            self.capacity = want
+
+    def steady(self, target_shape_dtype) -> bool:
+        """True when the next step of this camera signature replays captured graphs (or graphs are off): nothing left to
+        warm up.  `target_shape_dtype` = (tuple(target.shape), target.dtype) of the images passed to train_step."""
+        if not (self.use_graphs and self.cuda):
+            return True
+        e = self._graphs.get(self._key() + (target_shape_dtype,))
+        return e is not None and e["gA"] is not None and e["gB"] is not None
+
     def finish(self):
         """Order the caller's stream after everything queued so far, the SH update on the side stream included (call
         before reading parameters)."""

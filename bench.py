@@ -483,6 +483,9 @@ def run_gpu_arm(args):
         targets[:] = [t.to(dev).float() / 255 for t in targets_u8]
         cam_rows[:] = [torch.cat([c["viewmat"].reshape(-1), c["lin_vel"], c["ang_vel"], c["cam_pos"]]).contiguous() for c in cams]
         stepper.staged = None
+        # every rank now knows every image's entry count: size the lists once, identically everywhere, so that no rank
+        # grows them (= captures new graphs, ~10 ms, which its peers then wait for in the next allreduce) later on
+        trainer.reserve(max(costs))
 
     # ---- kernel-resident metric: inputs already in HBM, CUDA-event timing, max over ranks
     # warm-up: at least one pass over every training image, so no timed step meets a new camera (first-use allocations,
@@ -490,6 +493,25 @@ def run_gpu_arm(args):
     n_warm = max(args.warmup, n_img + 4)  # (+ the two eager rounds before the pipelined trainer captures its graphs)
     for w in range(n_warm):
         stepper.step(w)
+    # ... and until the trainer is steady: the list capacity follows a high-water mark that the host learns one step late,
+    # a growth means two eager steps and a graph capture (~10 ms) -- if the image that triggers it comes late in the pass,
+    # the capture would land in the timed region (r3n8: one 11.7 ms step among twenty of 1.4 ms at N = 8, where eight ranks
+    # make a late trigger eight times as likely and every rank waits for the one that captures).  Whole extra passes, the
+    # ranks agree on them (a rank that went on alone would deadlock the exchange), at most three.
+    if pipelined:
+        sig = (tuple(targets[0].shape), targets[0].dtype)
+        for _ in range(3):
+            cap0 = trainer.capacity
+            trainer.finish()
+            trainer.sync_status()
+            more = torch.tensor([0 if (trainer.capacity == cap0 and trainer.steady(sig)) else 1], device=dev)
+            if world > 1:
+                dist.all_reduce(more, op=dist.ReduceOp.MAX)
+            if int(more.item()) == 0:
+                break
+            for w in range(n_img):
+                stepper.step(n_warm + w)
+            n_warm += n_img
     # the clock sampler forks nvidia-smi: start it BEFORE the barrier that opens the timed region (round 1 started it
     # on rank 0 after the barrier, so the other ranks waited for rank 0's fork/exec inside their first allreduce and
     # that latency was charged to the max-over-ranks time)

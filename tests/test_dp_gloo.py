@@ -194,6 +194,12 @@ def _pipelined_worker(rank, world, port, out):
     t1.train_step(tgt)
     t1.finish()
     assert not torch.equal(m1.flat.detach(), before)
+    # reserve(): lists sized once from a known entry count (same number on every rank); never shrinks; steady() is
+    # trivially true without CUDA graphs
+    t1.reserve(1000)
+    assert t1.capacity == 131072 and t1.steady(((scene["H"], scene["W"], 3), torch.float32))
+    t1.reserve(10)
+    assert t1.capacity == 131072
     if rank == 0:
         torch.save(m1.flat.clone(), out)
     dist.destroy_process_group()
