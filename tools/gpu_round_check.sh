@@ -23,4 +23,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:blend_backward_kernel -c 1 -o gpurun_out/prof_bwd_${TAG} -f python tools/blend_probe.py --reps 1 --what bwd > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:blend_forward_kernel -c 1 -o gpurun_out/prof_fwd_${TAG} -f python tools/blend_probe.py --reps 1 --what fwd > /dev/null 2>&1
 fi
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_refarm.json 2> gpurun_out/${TAG}_refarm.err; tail -c 400 gpurun_out/${TAG}_refarm.json
+python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-ref-gpu --no-fused-path --timeline gpurun_out/${TAG}_timeline_n1.tsv > gpurun_out/${TAG}_bench_tl.json 2>/dev/null
 ls -la gpurun_out/*${TAG}* | head -20
