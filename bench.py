@@ -500,11 +500,14 @@ def run_gpu_arm(args):
     # ranks agree on them (a rank that went on alone would deadlock the exchange), at most three.
     if pipelined:
         sig = (tuple(targets[0].shape), targets[0].dtype)
-        for _ in range(3):
+        for attempt in range(3):
             cap0 = trainer.capacity
             trainer.finish()
             trainer.sync_status()
-            more = torch.tensor([0 if (trainer.capacity == cap0 and trainer.steady(sig)) else 1], device=dev)
+            unsteady = not (trainer.capacity == cap0 and trainer.steady(sig))
+            if attempt == 0 and os.environ.get("B200_BENCH_FORCE_EXTRA_PASS") == "1":
+                unsteady = True  # (exercises the extra-pass branch on a box where the trainer is already steady)
+            more = torch.tensor([1 if unsteady else 0], device=dev)
             if world > 1:
                 dist.all_reduce(more, op=dist.ReduceOp.MAX)
             if int(more.item()) == 0:
