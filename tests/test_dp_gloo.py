@@ -205,10 +205,11 @@ def _pipelined_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_pipelined_trainer_gloo(tmp_path):
-    """world 2: the pipelined trainer (geometry phase of image k+1 issued before the SH slice of step k is updated) ends
+@pytest.mark.parametrize("world", [2, 4])
+def test_pipelined_trainer_gloo(tmp_path, world):
+    """world 2 / 4: the pipelined trainer (geometry phase of image k+1 issued before the SH slice of step k is updated) ends
     at the same parameters as the plain trainer, replicas stay identical, and an overflow on one rank vetoes the step on
     all of them."""
     out = str(tmp_path / "flat2.pt")
-    mp.spawn(_pipelined_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_pipelined_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert torch.isfinite(torch.load(out)).all()
