@@ -8,11 +8,13 @@
 //     product and last-contributor index live in registers) instead of S walks;
 //   * per-Gaussian gradients are accumulated over the S samples in registers BEFORE the warp
 //     reduction: S x fewer shuffles and atomics than backward.cu:334-365;
-//   * the 13 per-Gaussian sums are reduced with a 16-shuffle transposing butterfly (instead of
-//     13 x 5 shuffles) that leaves each sum on its own lane, so the 13 atomics issue as one
-//     predicated RED instruction instead of 13 serial ones from lane 0;
+//   * the 13 per-Gaussian sums of a visit are reduced over the warp through a shared-memory
+//     transposition (packed kernel: 13 STS + 4 LDS.128 + 7 packed adds + 1 shuffle) or a 16-shuffle
+//     transposing butterfly (generic kernel) instead of 13 x 5 shuffles; either way each sum ends on
+//     its own lane, so the 13 atomics issue as ONE predicated RED instruction instead of 13 serial
+//     ones from lane 0;
 //   * the same per-warp rectangle cull and TMA-bulk staged 64-byte records as the forward.
-// Bound: FP32 issue, MUFU, SHFL and L2 atomic throughput -- not HBM; see DESIGN.md.
+// Bound: FP32 issue, MUFU, LSU and L2 atomic throughput -- not HBM; see DESIGN.md section 4.
 #include "blend_common.cuh"
 
 namespace b200 {
